@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched delivery_drone simulator (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # ours (CUDA, sm_100a)
+    python bench.py --impl reference [--gpus N] --steps K ...      # the reference's CPU path (port)
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[2]): 1,048,576 drone envs per GPU, auto-reset with Philox spawn
+randomisation of drone and platform, 250-step truncation, synthetic random actions (p = 0.5 per
+thruster) read from a pre-generated device trace.  One "step" = one DroneGame.step for every env
+of one 1M-env shard = ONE launch of the fused step kernel.  The state of one shard (~56 MB, ~116 MB
+with observations) would sit in the 126 MB L2, so the GPU holds SHARDS independent 1M-env shards
+and consecutive steps rotate over them: every launch streams its state from HBM (working set
+SHARDS x ~116 MB > L2).  All shards are real, distinct environments (own global env ids).
+
+Printed JSON line (rank 0): value = env-steps/s over all ranks for the gym-surface step (obs +
+reward + flags written, 146 algorithmic B/env-step); `variants` carries the step-only (86 B) and
+T-steps-per-launch numbers; `e2e` = the same step through HOST buffers (pinned H2D of actions, D2H
+of obs/reward/flags each step); `roofline` for the dominant kernel; `cpu_baseline` = the
+reference-faithful Python port stepped by os.cpu_count() processes on this box.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 1 << 20
+MAX_STEPS = 250
+BYTES_STEP_ONLY = 86      # read 44 + action 1, write 36 + reward 4 + flags 1
+BYTES_GYM = 146           # + 60 B observation row
+WORKLOAD = ("1M drone envs per GPU, auto-reset + spawn randomisation (drone+platform), max_steps 250, "
+            "synthetic random actions from a device trace")
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (NVML in a thread; no subprocess, no GPU work)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period, self._stop, self._thr, self.h = period_s, threading.Event(), None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    index = int(vis.split(",")[index])
+                except ValueError:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:          # NVML missing: report it, do not fail the bench
+            self.err = repr(e)
+
+    def _one(self):
+        nv = self.nv
+        self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for bit, name in self.REASONS.items():
+            if r & bit and name != "gpu_idle":
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._one()
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.h is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the CPU reference arm: reference-faithful Python port, one process per host core
+# ---------------------------------------------------------------------------------------------
+def cpu_port_multiprocess(ticks: int, warmup_ticks: int, procs: int | None = None, games: int = 6):
+    """BASELINE.json configs[0]: 6 DroneGame instances per process, random actions, 250-step cap.
+    Returns (env_steps_per_s aggregate, per-process mean, procs, seconds)."""
+    import multiprocessing as mp
+    from oracle.drone_port import cpu_rollout_worker
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(cpu_rollout_worker, [(p, ticks, games, MAX_STEPS, warmup_ticks) for p in range(procs)])
+    steps = sum(n for n, _ in res)
+    slowest = max(s for _, s in res)
+    per_proc = sum(n / s for n, s in res) / procs
+    return steps / slowest, per_proc, procs, slowest
+
+
+def c_oracle_threads(n: int, T: int, threads: int | None = None):
+    """The C float64 restatement (oracle/drone_oracle.c) on all host cores: env-steps/s."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_oracle as co
+    threads = threads or os.cpu_count() or 1
+    b = co.OracleBatch(n, seed=0, randomize_drone=True, randomize_platform=True, max_steps=MAX_STEPS, auto_reset=True)
+    b.reset()
+    cuts = [n * i // threads for i in range(threads + 1)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:     # ctypes releases the GIL inside the C call
+        list(ex.map(lambda k: b.rollout(T, policy=co.POL_RANDOM, lo=cuts[k], hi=cuts[k + 1]), range(threads)))
+    return n * T / (time.perf_counter() - t0), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    K, W = args.steps, args.warmup
+    # one "step" = `tps` ticks of (6 games x P processes); sized so K steps take ~10 s of CPU work
+    rate_guess = 7000.0                                   # ticks/s/process of the Python port
+    tps = max(1, int(math.ceil(10.0 * rate_guess / max(K, 1))))
+    tps = min(tps, max(1, int(120.0 * rate_guess / max(K + W, 1))))   # never more than ~2 min in total
+    agg, per_proc, procs, secs = cpu_port_multiprocess(K * tps, W * tps)
+    sample = (f"{procs} processes x 6 PortDroneGame (reference-faithful Python port of DroneGame), random actions, "
+              f"250-step cap, {K} steps x {tps} ticks x {6 * procs} envs = {K * tps * 6 * procs} env-steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": agg, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_sample": sample},
+        "cpu_baseline": {"value": agg, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                         "per_process": per_proc},
+        "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    dd = importlib.import_module("reinforcement-learning-101_b200")
+
+    rank, local, ws = dd.init_from_env("nccl")
+    if ws != args.gpus and ws > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K, W, S, n = args.steps, args.warmup, args.shards, args.envs
+    peak_gbs, peak_src = _peaks()
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if ws == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- SHARDS independent 1M-env shards per GPU; global env ids are unique over the whole job ----
+    envs = [dd.BatchedDroneEnv(n, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                               max_steps=MAX_STEPS, auto_reset=True, dtype=torch.float32,
+                               env_id_base=(rank * S + s) * n) for s in range(S)]
+    for e in envs:
+        e.reset()
+    TRACE = 64                                            # steps of pre-generated actions per shard
+    traces = [e.random_actions(TRACE) for e in envs]
+    launches = 0
+
+    def eager_steps(k0: int, k: int, want_obs: bool):
+        for j in range(k0, k0 + k):
+            s = j % S
+            envs[s].step_raw(traces[s][(j // S) % TRACE], want_obs=want_obs)
+
+    def timed(fn_warm, fn_run):
+        fn_warm()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn_run()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # CUDA graph of G consecutive steps (a whole number of shard rotations) removes the host launch cost
+    G = S * max(1, min(TRACE, 96 // S))
+
+    def make_graph(want_obs: bool):
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            eager_steps(0, S, want_obs)                   # warm the capture stream
+            with torch.cuda.graph(g, stream=side):
+                eager_steps(0, G, want_obs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return g
+
+    def run_steps(g, k: int, want_obs: bool):
+        q, r = divmod(k, G)
+        for _ in range(q):
+            g.replay()
+        eager_steps(0, r, want_obs)
+
+    sampler = ClockSampler(local)
+    results = {}
+    for name, want_obs in (("gym_step", True), ("step_only", False)):
+        g = make_graph(want_obs)
+        if name == "gym_step":
+            sampler.start()
+        ms = timed(lambda: run_steps(g, max(W, 3), want_obs), lambda: run_steps(g, K, want_obs))
+        if name == "gym_step":
+            sampler.stop()
+        launches += K
+        results[name] = ms
+        del g
+    # if the timed region was too short for NVML to see it, sample clocks over an untimed re-run
+    if sampler.h is not None and len(sampler.samples) < 5:
+        g = make_graph(True)
+        sampler.start()
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            run_steps(g, G * 8, True)
+            torch.cuda.synchronize(dev)
+        sampler.stop()
+        del g
+
+    # ---- T-steps-per-launch rollout kernel (state in registers; Philox actions in-kernel) ----
+    T_ROLL = 50
+    reps = max(1, K // T_ROLL // S) * S
+
+    def run_rollouts(k):
+        for j in range(k):
+            envs[j % S].rollout(T_ROLL, "random", t0=(j // S) * T_ROLL)
+    ms_roll = timed(lambda: run_rollouts(S), lambda: run_rollouts(reps))
+    launches += reps
+
+    # ---- e2e: HOST buffers in, HOST buffers out, every step ----
+    io = [envs[s].make_host_io() for s in range(min(S, 2))]
+    host_trace = traces[0][:TRACE].cpu().pin_memory()
+    Ke = max(3, min(K, args.e2e_steps))
+
+    def run_e2e(k):
+        for j in range(k):
+            b = io[j % len(io)]
+            b["actions"].copy_(host_trace[j % TRACE])     # host-side: the caller's actions of this step
+            envs[j % S].step_host(b)
+    t0 = None
+
+    def run_e2e_timed():
+        run_e2e(Ke)
+    ms_e2e = timed(lambda: run_e2e(3), run_e2e_timed)
+    launches += Ke
+    h2d = n * 1
+    d2h = n * (envs[0].obs_stride * 4 + 4 + 1)
+
+    stats = None
+    for e in envs[:1]:
+        stats = e.stats(reduce=ws > 1)
+
+    if rank == 0:
+        ms = results["gym_step"]
+        value = n * K * ws / (ms * 1e-3)
+        per_launch_s = ms * 1e-3 / K
+        achieved = n * BYTES_GYM / per_launch_s / 1e9
+        so_ms = results["step_only"]
+        so_achieved = n * BYTES_STEP_ONLY / (so_ms * 1e-3 / K) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu_per_step": n, "shards_per_gpu": S,
+                       "l2": f"inputs larger than L2: steps rotate over {S} independent {n}-env shards "
+                             f"({S} x ~{n * 116 >> 20} MiB state+outputs > 126 MB L2)",
+                       "launch": f"CUDA graph of {G} step launches, replayed", "parallelism": f"env-sharded x{ws}, no per-step comms"},
+            "roofline": {"bound": "hbm", "kernel": "step_kernel<float,AUTO,OBS>", "achieved": achieved, "peak": peak_gbs,
+                         "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n},
+            "variants": {
+                "step_only": {"value": n * K * ws / (so_ms * 1e-3), "ms_per_step": so_ms / K,
+                              "algorithmic_bytes_per_env_step": BYTES_STEP_ONLY, "achieved_gbs": so_achieved,
+                              "frac": so_achieved / peak_gbs},
+                "rollout_T50_in_kernel_actions": {"value": n * T_ROLL * reps * ws / (ms_roll * 1e-3),
+                                                  "ms_per_launch": ms_roll / reps, "steps_per_launch": T_ROLL},
+            },
+            "e2e": {"value": n * Ke * ws / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e2e / Ke,
+                    "api": "BatchedDroneEnv.step_host (pinned host actions in; obs, reward, flags out)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "episode_stats_shard0": stats,
+        }
+        if ws == 1 and not args.no_cpu_baseline:
+            ticks = args.cpu_ticks
+            agg, per_proc, procs, secs = cpu_port_multiprocess(ticks, 200)
+            c_rate, c_thr = c_oracle_threads(1 << 16, 250)
+            line["cpu_baseline"] = {
+                "value": agg, "unit": UNIT, "cores": procs, "kind": "port",
+                "sample": f"{procs} processes x 6 PortDroneGame x {ticks} ticks (random actions, 250-step cap), {secs:.1f} s",
+                "per_process": per_proc,
+                "c_oracle": {"value": c_rate, "threads": c_thr, "sample": "65,536 envs x 250 steps, float64 C restatement"},
+            }
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=12000)
+    ap.add_argument("--warmup", type=int, default=600)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per shard (= per step launch)")
+    ap.add_argument("--shards", type=int, default=6, help="independent shards per GPU that steps rotate over")
+    ap.add_argument("--e2e-steps", type=int, default=300)
+    ap.add_argument("--cpu-ticks", type=int, default=80000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

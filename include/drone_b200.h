@@ -1,0 +1,168 @@
+/*
+ * drone_b200.h -- C ABI of the B200-native batched delivery_drone simulator.
+ *
+ * Plain C, plain pointers and sizes, no torch types.  Every entry point is a pure
+ * function over caller-owned DEVICE buffers: no global state, no allocation, no
+ * host synchronisation; work is enqueued on the cudaStream_t passed in (as void*).
+ * Return value: 0 = ok, < 0 = argument error (DD_E_*), > 0 = cudaError_t.
+ * Safe to call concurrently on different streams / devices.
+ *
+ * The reference has no FFI: its "operator interface" for this path is the Python
+ * class DroneGame (/root/reference/delivery_drone/game/game_engine.py).  Each entry
+ * point below names the reference method(s) it replaces.
+ */
+#ifndef DRONE_B200_H
+#define DRONE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_ABI_VERSION 1
+
+/* ---- flag byte (per-step output and persistent state) ---------------------- */
+#define DD_DONE        0x01u   /* game_engine.py:53  self.done            */
+#define DD_LANDED      0x02u   /* drone.py:32        drone.landed         */
+#define DD_CRASHED     0x04u   /* drone.py:31        drone.crashed        */
+#define DD_TRUNCATED   0x08u   /* notebook-side time-out, Actor_Critic_PPO.ipynb c16:L89-93 */
+#define DD_CAUSE_MASK  0x30u
+#define DD_CAUSE_GROUND 0x10u  /* game_engine.py:193-197 */
+#define DD_CAUSE_FUEL   0x20u  /* game_engine.py:200-204 */
+#define DD_CAUSE_OOB    0x30u  /* game_engine.py:206-210 */
+
+/* ---- action byte ------------------------------------------------------------ */
+#define DD_ACT_MAIN   0x01u    /* action['main_thrust']  game_engine.py:115 */
+#define DD_ACT_LEFT   0x02u    /* action['left_thrust']  game_engine.py:116 */
+#define DD_ACT_RIGHT  0x04u    /* action['right_thrust'] game_engine.py:117 */
+#define DD_ACT_SKIP   0x80u    /* env not stepped this call (per-game stepping of the socket API) */
+
+/* ---- precision of the state / arithmetic ----------------------------------- */
+#define DD_F32 0               /* throughput instantiation (north_star: fp32 within 1e-5) */
+#define DD_F64 1               /* exact-parity instantiation (reference arithmetic is float64) */
+
+/* ---- built-in action sources of dd_rollout ---------------------------------- */
+#define DD_POLICY_TRACE    0   /* actions[t*n + i]                                         */
+#define DD_POLICY_RANDOM   1   /* Philox bits, p = 0.5 per thruster (examples/random_agent.py:27-31) */
+#define DD_POLICY_BANGBANG 2   /* main = vy > 1.5                       */
+
+#define DD_OBS_DIM      15     /* policy input, Actor_Critic_PPO.ipynb c10:L3-19           */
+#define DD_STATS_SLOTS  64     /* contention-spreading copies of the stats block           */
+#define DD_STATS_WORDS  8
+#define DD_RETURN_FIXED_SCALE 1048576.0   /* sum_return is accumulated as int64 in units of 2^-20 */
+
+/* error codes */
+#define DD_E_NULL    (-1)
+#define DD_E_RANGE   (-2)
+#define DD_E_DTYPE   (-3)
+#define DD_E_ALIGN   (-4)
+
+/* All of config.py that the headless path reads (config.py:4-5,18-68).  Doubles;
+ * the kernels derive their float / double constants from it on the host. */
+typedef struct DDParams {
+    double width, height;                 /* config.py:4-5   800, 600 */
+    double gravity, drag, angular_drag;   /* config.py:18-20 0.3, 0.99, 0.95 */
+    double drone_height;                  /* config.py:24    20 */
+    double main_thrust, side_thrust;      /* config.py:25-26 0.6, 0.3 */
+    double max_fuel, fuel_main, fuel_side;/* config.py:27-29 1000, 2, 1 */
+    double platform_w, platform_h;        /* config.py:32-33 100, 20 */
+    double land_speed, land_angle;        /* config.py:39-40 3.0, 20.0 */
+    double oob_margin;                    /* config.py:45    50 */
+    double ground_margin;                 /* game_engine.py:254 WINDOW_HEIGHT - 50 */
+    double r_land, r_crash, r_fuel, r_oob, r_step;  /* config.py:54-58 */
+    double shape_offset, shape_div;       /* game_engine.py:214 (500 - d) / 5000 */
+    double start_x, start_y;              /* config.py:61-62 400, 100 */
+    double plat_default_x, plat_default_y;/* game_engine.py:85 400, 500 */
+    double spawn_x_min, spawn_x_count;    /* game_engine.py:66 randint(100, 701)  -> 100, 601 */
+    double spawn_y_min, spawn_y_count;    /* game_engine.py:67 randint(50, 251)   -> 50, 201  */
+    double plat_x_min, plat_x_count;      /* game_engine.py:74-77 randint(100, 700) -> 100, 600 */
+    double plat_y_min, plat_y_count;      /* game_engine.py:78-81 randint(100, 550) -> 100, 450 */
+    double vel_norm, angle_norm, angvel_norm;  /* game_engine.py:156-159 10, 180, 10 */
+} DDParams;
+
+/*
+ * Environment state in HBM: structure of arrays, one entry per environment.
+ * R = float (DD_F32) or double (DD_F64).
+ *   pos_vel  : R[n][4] = x, y, vx, vy                  (drone.py:19-24)
+ *   att_fuel : R[n][4] = angle, angular_velocity, fuel, ep_return (drone.py:27-30, game_engine.py:51)
+ *   platform : R[n][2] = px, py                        (platform.py:19-20)
+ *   steps    : int32[n]                                (game_engine.py:50)
+ *   episode  : uint32[n] resets so far == Philox counter of the next spawn (game_engine.py:52)
+ *   flags    : uint8[n] persistent DD_* flags (non-zero only when auto_reset == 0)
+ * pos_vel / att_fuel must be 16-byte aligned, platform 8-byte (16 for DD_F64).
+ */
+typedef struct DDState {
+    void *pos_vel;
+    void *att_fuel;
+    void *platform;
+    int32_t *steps;
+    uint32_t *episode;
+    uint8_t *flags;
+    int32_t dtype;           /* DD_F32 / DD_F64 */
+} DDState;
+
+/* Per-call knobs shared by reset / step / rollout. */
+typedef struct DDEnvConfig {
+    uint64_t seed;           /* Philox key */
+    uint64_t env_id_base;    /* global id of env 0 of this shard: rank * n_local */
+    int32_t max_steps;       /* <= 0: no truncation */
+    int32_t auto_reset;      /* 0: freeze after done (game_engine.py:107-111); 1: same-step reset */
+    int32_t randomize_drone; /* DroneGame(randomize_drone=...)    game_engine.py:14 */
+    int32_t randomize_platform; /* DroneGame(randomize_platform=...) */
+} DDEnvConfig;
+
+int  dd_abi_version(void);
+void dd_default_params(DDParams *p);                 /* config.py defaults */
+const char *dd_error_string(int code);
+
+/* DroneGame.reset (game_engine.py:59-93) for every env with mask[i] != 0 (mask == NULL: all).
+ * obs (nullable): R[n][obs_stride] first observation of the new episode. */
+int dd_reset(const DDState *s, const DDParams *p, const DDEnvConfig *c, const uint8_t *mask,
+             void *obs, int32_t obs_stride, int64_t n, void *stream);
+
+/* DroneGame.step + get_state (+ reset when auto_reset) (game_engine.py:95-177).
+ *   actions    uint8[n]  DD_ACT_* bits
+ *   obs        R[n][obs_stride] or NULL (step-only)        game_engine.py:140-177
+ *   reward     R[n] or NULL                                game_engine.py:179-216
+ *   done_flags uint8[n] or NULL: flags of THIS step (non-zero iff the episode ended on it)
+ *   final_obs  R[n][obs_stride] or NULL: terminal observation, written only for envs that ended
+ *   stats      uint64[DD_STATS_SLOTS][DD_STATS_WORDS] or NULL: accumulated episode statistics */
+int dd_step(const DDState *s, const DDParams *p, const DDEnvConfig *c, const uint8_t *actions,
+            void *obs, int32_t obs_stride, void *reward, uint8_t *done_flags, void *final_obs,
+            uint64_t *stats, int64_t n, void *stream);
+
+/* T steps in one launch, state held in registers (collect_episodes inner loop without a policy
+ * network; Actor_Critic_PPO.ipynb c16:L42-108).  Optional [T][n] outputs. */
+int dd_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, int32_t policy,
+               const uint8_t *actions_tn, uint32_t t0, int32_t T,
+               void *reward_tn, uint8_t *done_tn, void *obs_tn, int32_t obs_stride,
+               uint64_t *stats, int64_t n, void *stream);
+
+/* [T][n] synthetic random action trace (same bits DD_POLICY_RANDOM uses in-kernel). */
+int dd_fill_random_actions(uint8_t *actions_tn, uint64_t seed, uint64_t env_id_base,
+                           uint32_t t0, int32_t T, int64_t n, void *stream);
+
+/* actions3[n][3] (any non-zero byte = pressed, game_engine.py:114-118) -> packed uint8[n]. */
+int dd_pack_actions(const uint8_t *actions3, uint8_t *packed, int64_t n, void *stream);
+
+/* Collapse the DD_STATS_SLOTS copies into out[DD_STATS_WORDS] (device):
+ *   0 episodes, 1 landed, 2 crashed, 3 truncated, 4 sum_return (int64, 2^-20 units),
+ *   5 sum_length, 6 env_steps, 7 reserved.  (Actor_Critic_PPO.ipynb c21:L94-95,L158-159,L169) */
+int dd_stats_collapse(const uint64_t *stats, uint64_t *out, void *stream);
+
+/* n, sum x, sum x^2 of a float vector into out[3] (device doubles); ACCUMULATES into out.
+ * (advantage normalisation moments, Actor_Critic_PPO.ipynb c21:L105) */
+int dd_moments(const float *x, int64_t n, double *out, void *stream);
+
+/* y = (x - mean) / (std + eps) with mean/std from moments[3] (unbiased std like torch.std). */
+int dd_normalize(const float *x, float *y, const double *moments, double eps, int64_t n, void *stream);
+
+/* compute_gae (Actor_Critic_PPO.ipynb c15:L49-53) for [T][n] rewards/dones and [T+1][n] values. */
+int dd_gae(const float *rewards_tn, const float *values_t1n, const uint8_t *dones_tn, float *adv_tn,
+           float *returns_tn, double gamma, double lambda, int32_t T, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONE_B200_H */

@@ -300,19 +300,24 @@ def obs_vector(state: dict) -> np.ndarray:
 # ---------------------------------------------------------------------------
 def cpu_rollout_worker(args):
     """One process: ``games`` instances, uniform random actions, reset on done
-    or after ``cap`` steps, for ``ticks`` ticks.  Returns (env_steps, seconds)."""
+    or after ``cap`` steps, for ``ticks`` timed ticks after ``warmup`` untimed ones (optional
+    fifth element).  Returns (env_steps, seconds)."""
     import time
 
-    seed, ticks, games, cap = args
+    seed, ticks, games, cap = args[:4]
+    warmup = args[4] if len(args) > 4 else 0
     np.random.seed(seed)
     rng = np.random.default_rng(seed)
     envs = [PortDroneGame(None, True, True) for _ in range(games)]
     for e in envs:
         e.reset()
-    acts = rng.integers(0, 2, (ticks, games, 3))
+    acts = rng.integers(0, 2, (ticks + warmup, games, 3))
     t0 = time.perf_counter()
     n = 0
-    for t in range(ticks):
+    for t in range(ticks + warmup):
+        if t == warmup:
+            t0 = time.perf_counter()
+            n = 0
         row = acts[t]
         for gi, e in enumerate(envs):
             a = row[gi]

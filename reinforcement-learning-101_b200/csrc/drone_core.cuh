@@ -1,0 +1,321 @@
+// drone_core.cuh -- the per-environment arithmetic of one DroneGame.step(), written once as
+// __host__ __device__ code and instantiated for float (throughput) and double (exact parity).
+//
+// This is a from-scratch statement of the reference's semantics, not a translation of its
+// object structure.  Reference anchors (/root/reference/delivery_drone/game/):
+//   drone.py:44-76     apply_thrust (sequential fuel gating)
+//   drone.py:78-103    update (gravity, drag, integrate, rotate, wrap)
+//   physics.py:6-23    rotate_point      physics.py:26-39 normalize_angle
+//   game_engine.py:179-279  reward priority: landing, ground, fuel, out of bounds, shaping
+//   game_engine.py:140-177  observation normalisation
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "../../include/drone_b200.h"
+
+#if defined(__CUDACC__)
+#define DD_HD __host__ __device__ __forceinline__
+#else
+#define DD_HD inline
+#endif
+
+namespace dd {
+
+// Constants derived on the host from DDParams, in the kernel's arithmetic type.
+template <typename R>
+struct Consts {
+    R gravity, drag, ang_drag;
+    R main_thrust, side_thrust, fuel_main, fuel_side, max_fuel;
+    R half_h;                       // drone_height / 2       drone.py:136
+    R plat_half_w, plat_half_h;     // platform.py:57-60
+    R land_speed, land_angle;
+    R ground_y;                     // height - ground_margin game_engine.py:254
+    R x_lo, x_hi, y_lo, y_hi;       // game_engine.py:275-279
+    R r_step, r_land, r_crash, r_fuel, r_oob;
+    R shape_offset, shape_div, inv_shape_div;
+    R width, height, vel_norm, angle_norm, angvel_norm;
+    R inv_width, inv_height, inv_vel, inv_angle, inv_angvel, inv_fuel;
+    R start_x, start_y, plat_x, plat_y;
+    R spawn_x_min, spawn_y_min, plat_x_min, plat_y_min;
+    uint32_t spawn_x_count, spawn_y_count, plat_x_count, plat_y_count;
+    // reach of the bottom-centre point from the body centre, for the cheap landing pre-test
+    R reach_x, reach_y;
+};
+
+template <typename R>
+inline Consts<R> make_consts(const DDParams& p) {
+    Consts<R> k;
+    k.gravity = (R)p.gravity; k.drag = (R)p.drag; k.ang_drag = (R)p.angular_drag;
+    k.main_thrust = (R)p.main_thrust; k.side_thrust = (R)p.side_thrust;
+    k.fuel_main = (R)p.fuel_main; k.fuel_side = (R)p.fuel_side; k.max_fuel = (R)p.max_fuel;
+    k.half_h = (R)(p.drone_height / 2);
+    k.plat_half_w = (R)(p.platform_w / 2); k.plat_half_h = (R)(p.platform_h / 2);
+    k.land_speed = (R)p.land_speed; k.land_angle = (R)p.land_angle;
+    k.ground_y = (R)(p.height - p.ground_margin);
+    k.x_lo = (R)(-p.oob_margin); k.x_hi = (R)(p.width + p.oob_margin);
+    k.y_lo = (R)(-p.oob_margin); k.y_hi = (R)(p.height + p.oob_margin);
+    k.r_step = (R)p.r_step; k.r_land = (R)p.r_land; k.r_crash = (R)p.r_crash;
+    k.r_fuel = (R)p.r_fuel; k.r_oob = (R)p.r_oob;
+    k.shape_offset = (R)p.shape_offset; k.shape_div = (R)p.shape_div; k.inv_shape_div = (R)(1.0 / p.shape_div);
+    k.width = (R)p.width; k.height = (R)p.height;
+    k.vel_norm = (R)p.vel_norm; k.angle_norm = (R)p.angle_norm; k.angvel_norm = (R)p.angvel_norm;
+    k.inv_width = (R)(1.0 / p.width); k.inv_height = (R)(1.0 / p.height);
+    k.inv_vel = (R)(1.0 / p.vel_norm); k.inv_angle = (R)(1.0 / p.angle_norm);
+    k.inv_angvel = (R)(1.0 / p.angvel_norm); k.inv_fuel = (R)(1.0 / p.max_fuel);
+    k.start_x = (R)p.start_x; k.start_y = (R)p.start_y;
+    k.plat_x = (R)p.plat_default_x; k.plat_y = (R)p.plat_default_y;
+    k.spawn_x_min = (R)p.spawn_x_min; k.spawn_y_min = (R)p.spawn_y_min;
+    k.plat_x_min = (R)p.plat_x_min; k.plat_y_min = (R)p.plat_y_min;
+    k.spawn_x_count = (uint32_t)p.spawn_x_count; k.spawn_y_count = (uint32_t)p.spawn_y_count;
+    k.plat_x_count = (uint32_t)p.plat_x_count; k.plat_y_count = (uint32_t)p.plat_y_count;
+    // + 1: slack so that no rounding of (px - x) can reject a state the exact box test accepts
+    k.reach_x = (R)(p.platform_w / 2 + p.drone_height / 2 + 1);
+    k.reach_y = (R)(p.platform_h / 2 + p.drone_height / 2 + 1);
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------
+// Arithmetic policy.  double: every product and sum rounded separately (no FMA contraction)
+// and true division, so results track the float64 reference to the last sin/cos ulp.
+// float: FMAs welcome, divisions by constants become reciprocal multiplies (<= 1.5 ulp).
+// ---------------------------------------------------------------------------------------
+template <typename R> struct Arith;
+
+template <> struct Arith<double> {
+    static DD_HD double mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dmul_rn(a, b);
+#else
+        return a * b;           // host build uses -ffp-contract=off
+#endif
+    }
+    static DD_HD double add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    static DD_HD double fma_(double a, double b, double c) { return add(mul(a, b), c); }   // never fused
+    static DD_HD double div(double a, double d, double /*inv_d*/) { return a / d; }
+    static DD_HD double sqrt_(double a) { return sqrt(a); }
+    static DD_HD double abs_(double a) { return fabs(a); }
+    // sin / cos of an angle in degrees: np.radians(a) == a * (pi / 180)   physics.py:16-18
+    static DD_HD void sincos_deg(double deg, double& s, double& c) {
+        const double rad = mul(deg, 3.14159265358979323846 / 180.0);
+#if defined(__CUDA_ARCH__)
+        sincos(rad, &s, &c);
+#else
+        s = sin(rad); c = cos(rad);
+#endif
+    }
+};
+
+template <> struct Arith<float> {
+    // Explicit roundings: the compiler may not contract or re-associate, so every kernel that
+    // inlines step_core (one step per launch, T steps per launch, fused policy) is bit-identical.
+#if defined(__CUDA_ARCH__)
+    static DD_HD float mul(float a, float b) { return __fmul_rn(a, b); }
+    static DD_HD float add(float a, float b) { return __fadd_rn(a, b); }
+    static DD_HD float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+    static DD_HD float mul(float a, float b) { return a * b; }
+    static DD_HD float add(float a, float b) { return a + b; }
+    static DD_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+    static DD_HD float div(float a, float /*d*/, float inv_d) { return mul(a, inv_d); }
+    static DD_HD float sqrt_(float a) { return sqrtf(a); }
+    static DD_HD float abs_(float a) { return fabsf(a); }
+    static DD_HD void sincos_deg(float deg, float& s, float& c) {
+#if defined(__CUDA_ARCH__)
+        // sin(pi * deg/180): exact range reduction, no radians rounding, <= 1 ulp each
+        sincospif(deg * (1.0f / 180.0f), &s, &c);
+#else
+        const double rad = (double)deg * (3.14159265358979323846 / 180.0);
+        s = (float)sin(rad); c = (float)cos(rad);
+#endif
+    }
+};
+
+template <typename R>
+struct Env {
+    R x, y, vx, vy;             // pos_vel
+    R angle, angvel, fuel, ret; // att_fuel
+    R px, py;                   // platform
+    int32_t steps;
+};
+
+// One DroneGame.step() for a live (not done) environment.  Returns the DD_* flags of this
+// step (0 = still flying) and the engine reward.  `speed` and `dist` come back because the
+// observation wants them too (game_engine.py:166,171).
+template <typename R>
+DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward, R& speed, R& dist)
+{
+    using A = Arith<R>;
+    R vx = e.vx, vy = e.vy, w = e.angvel, fuel = e.fuel;
+
+    // --- apply_thrust, drone.py:58-76: fuel re-tested before every thruster ------------
+    if ((act & DD_ACT_MAIN) && fuel > (R)0) {
+        R s, c;
+        A::sincos_deg(e.angle, s, c);                      // pre-update angle
+        vx = A::fma_(k.main_thrust, s, vx);                 // 0*c - (-0.6)*s    physics.py:20
+        vy = A::fma_(-k.main_thrust, c, vy);               // 0*s + (-0.6)*c    physics.py:21
+        fuel -= k.fuel_main;
+    }
+    if ((act & DD_ACT_LEFT) && fuel > (R)0) { w -= k.side_thrust; fuel -= k.fuel_side; }
+    if ((act & DD_ACT_RIGHT) && fuel > (R)0) { w += k.side_thrust; fuel -= k.fuel_side; }
+    fuel = fuel < (R)0 ? (R)0 : fuel;
+
+    // --- update, drone.py:88-103 (dt == 1) -------------------------------------------------
+    vy = A::add(vy, k.gravity);
+    vx = A::mul(vx, k.drag);
+    vy = A::mul(vy, k.drag);
+    const R x = A::add(e.x, vx);
+    const R y = A::add(e.y, vy);
+    R ang = A::add(e.angle, w);
+    w = A::mul(w, k.ang_drag);
+    while (ang > (R)180) ang -= (R)360;                    // physics.py:35-39
+    while (ang < (R)-180) ang += (R)360;
+
+    e.x = x; e.y = y; e.vx = vx; e.vy = vy; e.angle = ang; e.angvel = w; e.fuel = fuel;
+
+    // --- terminal tests, game_engine.py:185-216 ----------------------------------------------
+    speed = A::sqrt_(A::fma_(vx, vx, A::mul(vy, vy)));                 // drone.py:145
+    const R ddx = e.px - x, ddy = e.py - y;
+    dist = A::sqrt_(A::fma_(ddx, ddx, A::mul(ddy, ddy)));              // physics.py:44
+
+    uint32_t f = 0;
+    R r = k.r_step;
+    // Landing needs all of: bottom centre in the closed platform box, speed <= 3, |angle| <= 20
+    // (game_engine.py:224-242).  The bottom centre is at most half_h from the body centre, so
+    // the box test can only pass when |dx| <= w/2 + half_h and |dy| <= h/2 + half_h: test that
+    // (and the two cheap conditions) before paying for sin/cos of the post-update angle.
+    bool landed = false;
+    if (!(speed > k.land_speed) && A::abs_(ang) <= k.land_angle &&
+        A::abs_(ddx) <= k.reach_x && A::abs_(ddy) <= k.reach_y) {
+        R s, c;
+        A::sincos_deg(ang, s, c);
+        const R bx = A::fma_(-k.half_h, s, x);             // x + (0*c - 10*s)  drone.py:136-137
+        const R by = A::fma_(k.half_h, c, y);              // y + (0*s + 10*c)
+        landed = (e.px - k.plat_half_w <= bx) && (bx <= e.px + k.plat_half_w) &&
+                 (e.py - k.plat_half_h <= by) && (by <= e.py + k.plat_half_h);   // platform.py:74
+    }
+    if (landed) {
+        f = DD_DONE | DD_LANDED; r += k.r_land;
+    } else if (y > k.ground_y) {                           // game_engine.py:254-265
+        f = DD_DONE | DD_CRASHED | DD_CAUSE_GROUND; r += k.r_crash;
+    } else if (fuel <= (R)0) {                             // game_engine.py:200-204
+        f = DD_DONE | DD_CRASHED | DD_CAUSE_FUEL; r += k.r_fuel;
+    } else if (x < k.x_lo || x > k.x_hi || y < k.y_lo || y > k.y_hi) {   // :275-279
+        f = DD_DONE | DD_CRASHED | DD_CAUSE_OOB; r += k.r_oob;
+    } else {
+        r = A::add(r, A::div(k.shape_offset - dist, k.shape_div, k.inv_shape_div));   // :213-214
+    }
+    reward = r;
+    e.ret = A::add(e.ret, r);                              // game_engine.py:131
+    e.steps += 1;                                          // game_engine.py:132
+    return f;
+}
+
+// get_state(), game_engine.py:146-177, in the policy's key order (Actor_Critic_PPO.ipynb c10).
+// `put(j, v)` stores element j.
+template <typename R, typename Put>
+DD_HD void write_obs(const Env<R>& e, uint32_t flags, R speed, R dist, const Consts<R>& k, Put put)
+{
+    using A = Arith<R>;
+    put(0, A::div(e.x, k.width, k.inv_width));
+    put(1, A::div(e.y, k.height, k.inv_height));
+    put(2, A::div(e.vx, k.vel_norm, k.inv_vel));
+    put(3, A::div(e.vy, k.vel_norm, k.inv_vel));
+    put(4, A::div(e.angle, k.angle_norm, k.inv_angle));
+    put(5, A::div(e.angvel, k.angvel_norm, k.inv_angvel));
+    put(6, A::div(e.fuel, k.max_fuel, k.inv_fuel));
+    put(7, A::div(e.px, k.width, k.inv_width));
+    put(8, A::div(e.py, k.height, k.inv_height));
+    put(9, A::div(dist, k.width, k.inv_width));            // distance normalised by WIDTH (:166)
+    put(10, A::div(e.px - e.x, k.width, k.inv_width));
+    put(11, A::div(e.py - e.y, k.height, k.inv_height));
+    put(12, A::div(speed, k.vel_norm, k.inv_vel));
+    put(13, (flags & DD_LANDED) ? (R)1 : (R)0);
+    put(14, (flags & DD_CRASHED) ? (R)1 : (R)0);
+}
+
+template <typename R>
+DD_HD void speed_dist(const Env<R>& e, R& speed, R& dist)
+{
+    using A = Arith<R>;
+    speed = A::sqrt_(A::fma_(e.vx, e.vx, A::mul(e.vy, e.vy)));
+    const R ddx = e.px - e.x, ddy = e.py - e.y;
+    dist = A::sqrt_(A::fma_(ddx, ddx, A::mul(ddy, ddy)));
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: the spawn of episode k of
+// global env g under seed s is a pure function of (s, g, k), whatever the grid or GPU count.
+// ---------------------------------------------------------------------------------------
+struct U4 { uint32_t a, b, c, d; };
+
+DD_HD uint32_t mulhi_u32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+DD_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = mulhi_u32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi_u32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+// DroneGame.reset(), game_engine.py:59-93 + drone.py:221-238 + platform.py:104-114.
+// `episode` is the number of resets this env has had so far (the Philox counter).
+template <typename R>
+DD_HD void spawn(Env<R>& e, const Consts<R>& k, uint64_t seed, uint64_t env_id, uint32_t episode,
+                 bool rand_drone, bool rand_platform)
+{
+    e.x = k.start_x; e.y = k.start_y; e.px = k.plat_x; e.py = k.plat_y;
+    if (rand_drone || rand_platform) {
+        const U4 r = philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), episode, 0u,
+                                   (uint32_t)seed, (uint32_t)(seed >> 32));
+        if (rand_drone) {                                  // np.random.randint(lo, hi + 1)
+            e.x = k.spawn_x_min + (R)mulhi_u32(r.a, k.spawn_x_count);
+            e.y = k.spawn_y_min + (R)mulhi_u32(r.b, k.spawn_y_count);
+        }
+        if (rand_platform) {                               // np.random.randint(lo, hi)
+            e.px = k.plat_x_min + (R)mulhi_u32(r.c, k.plat_x_count);
+            e.py = k.plat_y_min + (R)mulhi_u32(r.d, k.plat_y_count);
+        }
+    }
+    e.vx = (R)0; e.vy = (R)0; e.angle = (R)0; e.angvel = (R)0;
+    e.fuel = k.max_fuel; e.ret = (R)0; e.steps = 0;
+}
+
+// 3-bit synthetic random action of step t (p = 0.5 per thruster).  One Philox call serves 32
+// consecutive steps: action j = t % 32 is bits [3j, 3j+3) of the 96-bit string a | b<<32 | c<<64.
+DD_HD U4 action_block(uint64_t seed, uint64_t env_id, uint32_t t)
+{
+    return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), t >> 5, 1u,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+DD_HD uint32_t action_from_block(const U4& r, uint32_t t)
+{
+    const uint32_t bit = 3u * (t & 31u), w = bit >> 5, sh = bit & 31u;
+    const uint32_t lo = w == 0 ? r.a : (w == 1 ? r.b : r.c);
+    const uint32_t hi = w == 0 ? r.b : (w == 1 ? r.c : r.d);
+    const uint64_t two = (uint64_t)lo | ((uint64_t)hi << 32);
+    return (uint32_t)(two >> sh) & 7u;
+}
+
+}  // namespace dd

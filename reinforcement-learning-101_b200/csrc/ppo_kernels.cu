@@ -1,0 +1,160 @@
+// ppo_kernels.cu -- the three HBM-bound reductions / scans that sit right after a rollout:
+//
+//   K4 moments_kernel    n, sum x, sum x^2 of the advantage buffer (one read of [T*n] floats)
+//      normalize_kernel  (x - mean) / (std + eps), unbiased std like torch.std
+//                        (Actor_Critic_PPO.ipynb c21:L105, Policy_Gradients.ipynb c26:L33-36)
+//   N3 gae_kernel        compute_gae backward scan, one thread per env, coalesced over n
+//                        (Actor_Critic_PPO.ipynb c15:L49-53)
+//
+// Streaming float work: float4 loads, grid = a whole number of waves over the 148 SMs, double
+// accumulation only in the per-thread / per-warp partials.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/drone_b200.h"
+
+namespace dd {
+
+constexpr int kRedBlock = 256;
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kRedBlock) moments_kernel(const float* __restrict__ x, int64_t n, double* out)
+{
+    __shared__ double s_s[kRedBlock / 32], s_q[kRedBlock / 32];
+    double s = 0.0, q = 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * kRedBlock + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kRedBlock;
+    // leading scalars until x is 16-byte aligned, then float4, then the tail
+    int64_t head = (int64_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(x) & 15u)) & 15u) / 4;
+    if (head > n) head = n;
+    const int64_t n4 = (n - head) / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x + head);
+    for (int64_t j = tid; j < n4; j += nthreads) {
+        const float4 v = __ldg(x4 + j);
+        // partial sums of 4 in float would lose bits; go to double per element
+        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    if (tid < head) { const double v = x[tid]; s += v; q += v * v; }
+    const int64_t tail0 = head + 4 * n4;
+    if (tid < n - tail0) { const double v = x[tail0 + tid]; s += v; q += v * v; }
+
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_s[w] = s; s_q[w] = q; }
+    __syncthreads();
+    if (w == 0) {
+        s = lane < kRedBlock / 32 ? s_s[lane] : 0.0;
+        q = lane < kRedBlock / 32 ? s_q[lane] : 0.0;
+        s = warp_sum_d(s); q = warp_sum_d(q);
+        if (lane == 0) {
+            atomicAdd(out + 1, s);
+            atomicAdd(out + 2, q);
+            if (blockIdx.x == 0) atomicAdd(out + 0, (double)n);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRedBlock) normalize_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const double* __restrict__ m, double eps, int64_t n)
+{
+    const double cnt = m[0], s = m[1], q = m[2];
+    const double mean = cnt > 0 ? s / cnt : 0.0;
+    double var = cnt > 1 ? (q - s * mean) / (cnt - 1.0) : 0.0;     // unbiased, torch.std default
+    var = var > 0 ? var : 0.0;
+    const float fmean = (float)mean;
+    const float inv = (float)(1.0 / (sqrt(var) + eps));
+    const int64_t tid = (int64_t)blockIdx.x * kRedBlock + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kRedBlock;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
+    if (vec) {
+        const int64_t n4 = n / 4;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* y4 = reinterpret_cast<float4*>(y);
+        for (int64_t j = tid; j < n4; j += nthreads) {
+            float4 v = __ldg(x4 + j);
+            v.x = (v.x - fmean) * inv; v.y = (v.y - fmean) * inv; v.z = (v.z - fmean) * inv; v.w = (v.w - fmean) * inv;
+            y4[j] = v;
+        }
+        if (tid < n - 4 * n4) y[4 * n4 + tid] = (x[4 * n4 + tid] - fmean) * inv;
+    } else {
+        for (int64_t j = tid; j < n; j += nthreads) y[j] = (x[j] - fmean) * inv;
+    }
+}
+
+// delta_t = r_t + gamma * V_{t+1} * (1 - done_t) - V_t ;  A_t = delta_t + gamma * lambda * (1 - done_t) * A_{t+1}
+// fp32 throughout, in the operation order of the torch original (python scalars gamma, gamma*lambda
+// are combined in double and rounded to fp32 when they meet the tensors).  No FMA contraction, so
+// the result is bit-identical to the eager torch loop.
+__global__ void __launch_bounds__(kRedBlock) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                         const uint8_t* __restrict__ done, float* __restrict__ adv,
+                                                         float* __restrict__ ret, float g, float gl, int32_t T, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kRedBlock + threadIdx.x;
+    if (i >= n) return;
+    float gae = 0.0f;
+    float v_next = __ldg(val + (int64_t)T * n + i);
+    // software prefetch one step ahead: the scan is a dependent chain only through `gae`
+    for (int32_t t = T - 1; t >= 0; --t) {
+        const int64_t o = (int64_t)t * n + i;
+        const float r = __ldg(rew + o), v = __ldg(val + o);
+        const float mask = done[o] ? 0.0f : 1.0f;
+        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, v_next), mask)), v);
+        gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, mask), gae));
+        adv[o] = gae;
+        if (ret) ret[o] = __fadd_rn(gae, v);
+        v_next = v;
+    }
+}
+
+static inline int wave_grid(int64_t work_items, int per_block, int max_waves_ctas)
+{
+    int64_t g = (work_items + per_block - 1) / per_block;
+    if (g > max_waves_ctas) g = max_waves_ctas;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace dd
+
+extern "C" {
+
+int dd_moments(const float* x, int64_t n, double* out, void* stream)
+{
+    if (!x || !out) return DD_E_NULL;
+    if (n < 0) return DD_E_RANGE;
+    if ((reinterpret_cast<uintptr_t>(x) & 3u) || (reinterpret_cast<uintptr_t>(out) & 7u)) return DD_E_ALIGN;
+    if (n == 0) return 0;
+    const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 4, dd::kSMs * 8);
+    dd::moments_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(x, n, out);
+    return (int)cudaGetLastError();
+}
+
+int dd_normalize(const float* x, float* y, const double* moments, double eps, int64_t n, void* stream)
+{
+    if (!x || !y || !moments) return DD_E_NULL;
+    if (n < 0) return DD_E_RANGE;
+    if (n == 0) return 0;
+    const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 2, dd::kSMs * 8);
+    dd::normalize_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(x, y, moments, eps, n);
+    return (int)cudaGetLastError();
+}
+
+int dd_gae(const float* rewards_tn, const float* values_t1n, const uint8_t* dones_tn, float* adv_tn,
+           float* returns_tn, double gamma, double lambda, int32_t T, int64_t n, void* stream)
+{
+    if (!rewards_tn || !values_t1n || !dones_tn || !adv_tn) return DD_E_NULL;
+    if (n < 0 || T < 0) return DD_E_RANGE;
+    if (n == 0 || T == 0) return 0;
+    const int grid = (int)((n + dd::kRedBlock - 1) / dd::kRedBlock);
+    dd::gae_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn,
+                                                                       (float)gamma, (float)(gamma * lambda), T, n);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

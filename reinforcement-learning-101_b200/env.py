@@ -1,0 +1,337 @@
+"""``BatchedDroneEnv`` -- the gym-style ``reset()/step()`` surface of the reference ``DroneGame``
+(/root/reference/delivery_drone/game/game_engine.py:14-298) for N environments at once, stepped by
+the sm_100a kernels behind the C ABI of ``include/drone_b200.h``.
+
+PyTorch is plumbing here: it owns the device buffers and the stream.  Every numeric result comes
+from ``libdrone_b200.so``; there is no Python / torch fallback for any of it.
+
+Semantics kept from the reference (file:line are under /root/reference/delivery_drone/game/):
+  * observation = the first 15 keys of ``get_state()`` in policy order (game_engine.py:146-177,
+    Actor_Critic_PPO.ipynb c10:L3-19); with ``obs_stride=16`` column 15 is ``steps`` (16th key)
+  * reward / termination priority of ``_calculate_reward`` (game_engine.py:179-216)
+  * ``auto_reset=False``: frozen after done -- reward 0, done stays True, no state change
+    (game_engine.py:107-111)
+  * action = any truthy value per thruster (game_engine.py:114-118)
+New, because the reference has neither: same-step auto-reset with Philox spawns, ``max_steps``
+truncation (the notebooks' time-out, Actor_Critic_PPO.ipynb c16:L89-93, without its client-side
+-500), and on-device episode statistics.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _native as nv
+
+_STATE_KEYS = ("x", "y", "vx", "vy", "angle", "angular_velocity", "fuel", "total_reward",
+               "platform_x", "platform_y", "steps", "episode", "flags")
+POLICIES = {"trace": nv.POLICY_TRACE, "random": nv.POLICY_RANDOM, "bangbang": nv.POLICY_BANGBANG}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class StepInfo(dict):
+    """``info`` of a batched step.  ``flags`` (uint8 DD_* bits of THIS step) is always present;
+    the derived boolean / counter views are materialised only when asked for."""
+
+    def __init__(self, env: "BatchedDroneEnv", flags: torch.Tensor):
+        super().__init__(flags=flags)
+        self._env = env
+
+    def __missing__(self, key):
+        f = dict.__getitem__(self, "flags")
+        if key == "landed":
+            v = (f & nv.LANDED) != 0
+        elif key == "crashed":
+            v = (f & nv.CRASHED) != 0
+        elif key == "truncated":
+            v = (f & nv.TRUNCATED) != 0
+        elif key == "cause":
+            v = (f & nv.CAUSE_MASK) >> 4
+        elif key == "steps":
+            v = self._env.steps
+        elif key == "episode_return":
+            v = self._env.att_fuel[:, 3]
+        elif key == "final_obs":
+            v = self._env.final_obs
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+
+class BatchedDroneEnv:
+    """N ``DroneGame`` instances on one GPU.
+
+    ``DroneGame(render_mode=None, randomize_drone=False, randomize_platform=True)`` defaults are
+    kept (game_engine.py:14).  ``dtype=torch.float64`` selects the exact-parity instantiation of the
+    kernels (the reference computes in float64); ``torch.float32`` is the throughput one.
+    """
+
+    def __init__(self, num_envs: int, device="cuda", seed: int = 0, randomize_drone: bool = False,
+                 randomize_platform: bool = True, max_steps: Optional[int] = None, auto_reset: bool = True,
+                 dtype: torch.dtype = torch.float32, env_id_base: int = 0, obs_stride: int = nv.OBS_DIM,
+                 want_final_obs: bool = False, params: Optional[nv.DDParams] = None):
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        if obs_stride not in (15, 16):
+            raise ValueError("obs_stride must be 15 or 16")
+        if num_envs < 0:
+            raise ValueError("num_envs must be >= 0")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("BatchedDroneEnv runs on a CUDA device only (there is no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = nv.lib()
+        self.num_envs = n = int(num_envs)
+        self.dtype = dtype
+        self.obs_stride = int(obs_stride)
+        self.params = params if params is not None else nv.default_params()
+        dev = self.device
+        # ---- state in HBM (layout: include/drone_b200.h DDState) ----
+        self.pos_vel = torch.zeros(n, 4, dtype=dtype, device=dev)      # x, y, vx, vy
+        self.att_fuel = torch.zeros(n, 4, dtype=dtype, device=dev)     # angle, angvel, fuel, ep_return
+        self.platform = torch.zeros(n, 2, dtype=dtype, device=dev)     # px, py
+        self.steps = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(n, dtype=torch.int32, device=dev)   # uint32 bit pattern
+        self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # ---- per-step outputs ----
+        self.obs = torch.zeros(n, self.obs_stride, dtype=dtype, device=dev)
+        self.reward = torch.zeros(n, dtype=dtype, device=dev)
+        self.step_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.final_obs = torch.zeros(n, self.obs_stride, dtype=dtype, device=dev) if want_final_obs else None
+        self._packed = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # ---- episode statistics (K3) ----
+        self.stats_slots = torch.zeros(nv.STATS_SLOTS, nv.STATS_WORDS, dtype=torch.int64, device=dev)
+        self._stats_out = torch.zeros(nv.STATS_WORDS, dtype=torch.int64, device=dev)
+
+        self._state = nv.DDState(self.pos_vel.data_ptr(), self.att_fuel.data_ptr(), self.platform.data_ptr(),
+                                 self.steps.data_ptr(), self.episode.data_ptr(), self.flags.data_ptr(),
+                                 nv.F32 if dtype == torch.float32 else nv.F64)
+        self._cfg = nv.DDEnvConfig(int(seed) & (2 ** 64 - 1), int(env_id_base), int(max_steps or 0),
+                                   int(bool(auto_reset)), int(bool(randomize_drone)), int(bool(randomize_platform)))
+        self._needs_reset = True
+
+    # ---- configuration ------------------------------------------------------------------------
+    @property
+    def seed(self) -> int:
+        return self._cfg.seed
+
+    @property
+    def env_id_base(self) -> int:
+        return self._cfg.env_id_base
+
+    @property
+    def max_steps(self) -> int:
+        return self._cfg.max_steps
+
+    @max_steps.setter
+    def max_steps(self, v: Optional[int]) -> None:
+        """Curriculum knob (Actor_Critic_PPO.ipynb c19:L13-17): takes effect on the next step."""
+        self._cfg.max_steps = int(v or 0)
+
+    @property
+    def auto_reset(self) -> bool:
+        return bool(self._cfg.auto_reset)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- DroneGame.reset ------------------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``DroneGame.reset()`` (game_engine.py:59-93) for all envs, or those with ``mask[i]`` set.
+        Returns the observation tensor ``[N, obs_stride]`` (rows of unmasked envs are refreshed too)."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device).ne(0).to(torch.uint8).contiguous()
+            if m.shape != (self.num_envs,):
+                raise ValueError("mask must have shape [num_envs]")
+            self.observe()                     # rows of unmasked envs: current state
+        nv.check(self._lib.dd_reset(C.byref(self._state), C.byref(self.params), C.byref(self._cfg), _ptr(m),
+                                    self.obs.data_ptr(), self.obs_stride, self.num_envs, self._stream()), "dd_reset")
+        self._needs_reset = False
+        return self.obs
+
+    def observe(self) -> torch.Tensor:
+        """``get_state()`` (game_engine.py:140-177) of every env without stepping."""
+        self._packed.fill_(nv.ACT_SKIP)
+        nv.check(self._lib.dd_step(C.byref(self._state), C.byref(self.params), C.byref(self._cfg),
+                                   self._packed.data_ptr(), self.obs.data_ptr(), self.obs_stride, None, None, None,
+                                   None, self.num_envs, self._stream()), "dd_step(observe)")
+        return self.obs
+
+    # ---- actions ----------------------------------------------------------------------------------
+    def pack_actions(self, actions: torch.Tensor) -> torch.Tensor:
+        """``[N]`` uint8 bit-packed actions pass through; ``[N,3]`` (main, left, right; any non-zero
+        value = pressed, game_engine.py:114-118) is packed on the device."""
+        a = actions
+        if a.device != self.device:
+            a = a.to(self.device, non_blocking=True)
+        if a.dim() == 1:
+            if a.dtype != torch.uint8:
+                a = a.to(torch.uint8)
+            if a.shape[0] != self.num_envs:
+                raise ValueError("actions must have shape [num_envs] or [num_envs, 3]")
+            return a.contiguous()
+        if a.shape != (self.num_envs, 3):
+            raise ValueError("actions must have shape [num_envs] or [num_envs, 3]")
+        if a.dtype == torch.bool:
+            a3 = a.contiguous().view(torch.uint8)
+        elif a.dtype == torch.uint8:
+            a3 = a.contiguous()
+        else:
+            a3 = a.ne(0).contiguous().view(torch.uint8)
+        nv.check(self._lib.dd_pack_actions(a3.data_ptr(), self._packed.data_ptr(), self.num_envs, self._stream()),
+                 "dd_pack_actions")
+        return self._packed
+
+    # ---- DroneGame.step -----------------------------------------------------------------------------
+    def step_raw(self, packed: torch.Tensor, want_obs: bool = True, stats: bool = True):
+        """One ``DroneGame.step`` per env: exactly one kernel launch, no other device work.
+        ``packed``: uint8 ``[N]`` on this device.  Returns ``(obs, reward, step_flags)`` -- the
+        env's own output buffers, overwritten by the next call."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")
+        nv.check(self._lib.dd_step(
+            C.byref(self._state), C.byref(self.params), C.byref(self._cfg), packed.data_ptr(),
+            self.obs.data_ptr() if want_obs else None, self.obs_stride, self.reward.data_ptr(),
+            self.step_flags.data_ptr(), _ptr(self.final_obs), self.stats_slots.data_ptr() if stats else None,
+            self.num_envs, self._stream()), "dd_step")
+        return self.obs, self.reward, self.step_flags
+
+    def step(self, actions: torch.Tensor):
+        """Gym-style: ``(obs [N,obs_stride], reward [N], done [N] bool, info)``.
+
+        ``auto_reset=True``: on the terminating step ``reward``/``done``/``info`` describe the finished
+        episode while ``obs`` is the first observation of the next one (``info['final_obs']`` holds the
+        terminal observation when the env was built with ``want_final_obs=True``).
+        ``auto_reset=False``: reference behaviour, frozen after done until ``reset()``."""
+        packed = self.pack_actions(actions)
+        obs, reward, flags = self.step_raw(packed)
+        done = (flags & nv.DONE) != 0
+        return obs, reward, done, StepInfo(self, flags)
+
+    # ---- T steps in one launch ---------------------------------------------------------------------
+    def rollout(self, T: int, policy: str = "random", actions: Optional[torch.Tensor] = None, t0: int = 0,
+                reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None,
+                obs_out: Optional[torch.Tensor] = None, stats: bool = True):
+        """T steps per launch with the env state in registers (one state round trip per launch).
+        ``policy``: 'trace' (``actions`` uint8 ``[T,N]``), 'random' (Philox, p=0.5 per thruster;
+        examples/random_agent.py:27-31) or 'bangbang' (main = vy > 1.5).  Optional ``[T,N]`` outputs."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before rollout()")
+        pol = POLICIES[policy]
+        n = self.num_envs
+        if pol == nv.POLICY_TRACE:
+            if actions is None or actions.dtype != torch.uint8 or tuple(actions.shape) != (T, n):
+                raise ValueError("policy='trace' needs uint8 actions of shape [T, num_envs]")
+            actions = actions.contiguous()
+        for name, t, shape in (("reward_out", reward_out, (T, n)), ("done_out", done_out, (T, n)),
+                               ("obs_out", obs_out, (T, n, self.obs_stride))):
+            if t is not None and (tuple(t.shape) != shape or not t.is_contiguous() or t.device != self.device):
+                raise ValueError(f"{name} must be a contiguous {shape} tensor on {self.device}")
+        if reward_out is not None and reward_out.dtype != self.dtype or obs_out is not None and obs_out.dtype != self.dtype:
+            raise ValueError("reward_out / obs_out must have the env dtype")
+        if done_out is not None and done_out.dtype != torch.uint8:
+            raise ValueError("done_out must be uint8")
+        nv.check(self._lib.dd_rollout(
+            C.byref(self._state), C.byref(self.params), C.byref(self._cfg), pol, _ptr(actions), int(t0), int(T),
+            _ptr(reward_out), _ptr(done_out), _ptr(obs_out), self.obs_stride,
+            self.stats_slots.data_ptr() if stats else None, n, self._stream()), "dd_rollout")
+
+    def random_actions(self, T: int, t0: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The ``[T,N]`` uint8 trace that ``policy='random'`` draws in-kernel."""
+        if out is None:
+            out = torch.empty(T, self.num_envs, dtype=torch.uint8, device=self.device)
+        nv.check(self._lib.dd_fill_random_actions(out.data_ptr(), self._cfg.seed, self._cfg.env_id_base, int(t0),
+                                                  int(T), self.num_envs, self._stream()), "dd_fill_random_actions")
+        return out
+
+    # ---- episode statistics (K3) --------------------------------------------------------------------
+    def stats_tensor(self) -> torch.Tensor:
+        """int64[8] on device: episodes, landed, crashed, truncated, sum_return (2^-20 units),
+        sum_length, env_steps, reserved -- accumulated since the last ``reset_stats()``."""
+        nv.check(self._lib.dd_stats_collapse(self.stats_slots.data_ptr(), self._stats_out.data_ptr(), self._stream()),
+                 "dd_stats_collapse")
+        return self._stats_out
+
+    def reset_stats(self) -> None:
+        self.stats_slots.zero_()
+
+    def stats(self, reduce: bool = False) -> Dict[str, float]:
+        """Host dict of the episode statistics (Actor_Critic_PPO.ipynb c21:L94-95,L158-159,L169);
+        ``reduce=True`` all-reduces the 8 words over the default process group first."""
+        from .distributed import allreduce_stats, stats_dict
+        w = self.stats_tensor()
+        if reduce:
+            w = allreduce_stats(w.clone())
+        return stats_dict(w)
+
+    # ---- checkpoint / injection -----------------------------------------------------------------------
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        """Copies of the raw (un-normalised) state, reference attribute names (drone.py:19-32,
+        platform.py:19-20, game_engine.py:50-53)."""
+        pv, af, pf = self.pos_vel, self.att_fuel, self.platform
+        return {
+            "x": pv[:, 0].clone(), "y": pv[:, 1].clone(), "vx": pv[:, 2].clone(), "vy": pv[:, 3].clone(),
+            "angle": af[:, 0].clone(), "angular_velocity": af[:, 1].clone(), "fuel": af[:, 2].clone(),
+            "total_reward": af[:, 3].clone(), "platform_x": pf[:, 0].clone(), "platform_y": pf[:, 1].clone(),
+            "steps": self.steps.clone(), "episode": self.episode.clone(), "flags": self.flags.clone(),
+        }
+
+    def set_state(self, state: Dict[str, torch.Tensor]) -> None:
+        """Overwrite any subset of the state tensors (each ``[N]``)."""
+        cols = {"x": (self.pos_vel, 0), "y": (self.pos_vel, 1), "vx": (self.pos_vel, 2), "vy": (self.pos_vel, 3),
+                "angle": (self.att_fuel, 0), "angular_velocity": (self.att_fuel, 1), "fuel": (self.att_fuel, 2),
+                "total_reward": (self.att_fuel, 3), "platform_x": (self.platform, 0), "platform_y": (self.platform, 1)}
+        for k, v in state.items():
+            if k not in _STATE_KEYS:
+                raise KeyError(k)
+            v = torch.as_tensor(v, device=self.device)
+            if k in cols:
+                buf, j = cols[k]
+                buf[:, j] = v.to(self.dtype)
+            else:
+                getattr(self, k).copy_(v.to(getattr(self, k).dtype))
+        self._needs_reset = False
+
+    def inject(self, x, y, platform_x, platform_y) -> torch.Tensor:
+        """``g.reset(); g.drone.reset(x, y); g.platform.reset(px, py)`` for every env (the parity
+        tests' way of starting from identical states).  Returns the observation."""
+        n, dev = self.num_envs, self.device
+        z = torch.zeros(n, dtype=self.dtype, device=dev)
+        self.set_state({
+            "x": x, "y": y, "platform_x": platform_x, "platform_y": platform_y,
+            "vx": z, "vy": z, "angle": z, "angular_velocity": z, "total_reward": z,
+            "fuel": torch.full((n,), float(self.params.max_fuel), dtype=self.dtype, device=dev),
+            "steps": torch.zeros(n, dtype=torch.int32, device=dev),
+            "flags": torch.zeros(n, dtype=torch.uint8, device=dev),
+            "episode": self.episode + 1,
+        })
+        return self.observe()
+
+    # ---- host-buffer entry point (what a CPU-side caller such as the socket shim uses) -----------------
+    def make_host_io(self):
+        """Pinned host buffers for ``step_host``."""
+        pin = dict(pin_memory=True)
+        return {
+            "actions": torch.zeros(self.num_envs, dtype=torch.uint8, **pin),
+            "obs": torch.zeros(self.num_envs, self.obs_stride, dtype=self.dtype, **pin),
+            "reward": torch.zeros(self.num_envs, dtype=self.dtype, **pin),
+            "flags": torch.zeros(self.num_envs, dtype=torch.uint8, **pin),
+        }
+
+    def step_host(self, io) -> None:
+        """HOST in / HOST out step: copies ``io['actions']`` (pinned, packed uint8) to the device,
+        steps, copies obs / reward / flags back into ``io`` and waits for them."""
+        self._packed.copy_(io["actions"], non_blocking=True)
+        self.step_raw(self._packed)
+        io["obs"].copy_(self.obs, non_blocking=True)
+        io["reward"].copy_(self.reward, non_blocking=True)
+        io["flags"].copy_(self.step_flags, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()

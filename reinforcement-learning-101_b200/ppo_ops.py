@@ -1,0 +1,66 @@
+"""Device ops that sit right after a rollout in the PPO notebook, each one C-ABI call:
+
+  * ``gae``                  compute_gae            (Actor_Critic_PPO.ipynb c15:L49-53), batched [T,N]
+  * ``advantage_moments``    n, sum, sum of squares (K4)
+  * ``normalize_advantages`` (adv - mean) / (std + 1e-8) with the UNBIASED std of torch.std
+                             (Actor_Critic_PPO.ipynb c21:L105), moments all-reduced over ranks
+
+No torch fallback: the arithmetic is in ``csrc/ppo_kernels.cu``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _native as nv
+from .distributed import allreduce_moments
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous CUDA tensor of dtype {dtype}")
+
+
+def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma: float = 0.99,
+        lambda_: float = 0.95, want_returns: bool = False):
+    """``rewards`` fp32 [T,N], ``values`` fp32 [T+1,N] (bootstrap row last), ``dones`` uint8 [T,N]
+    (non-zero = episode ended on that step).  Returns advantages [T,N] (and returns = adv + V)."""
+    _need(rewards, torch.float32, "rewards")
+    _need(values, torch.float32, "values")
+    _need(dones, torch.uint8, "dones")
+    T, n = rewards.shape
+    if tuple(values.shape) != (T + 1, n) or tuple(dones.shape) != (T, n):
+        raise ValueError("values must be [T+1,N] and dones [T,N]")
+    adv = torch.empty_like(rewards)
+    ret = torch.empty_like(rewards) if want_returns else None
+    nv.check(nv.lib().dd_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), adv.data_ptr(),
+                             None if ret is None else ret.data_ptr(), float(gamma), float(lambda_), T, n,
+                             _stream(rewards)), "dd_gae")
+    return (adv, ret) if want_returns else adv
+
+
+def advantage_moments(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """float64[3] on device: (n, sum x, sum x^2).  ACCUMULATES into ``out`` when given."""
+    _need(x, torch.float32, "x")
+    if out is None:
+        out = torch.zeros(3, dtype=torch.float64, device=x.device)
+    nv.check(nv.lib().dd_moments(x.data_ptr(), x.numel(), out.data_ptr(), _stream(x)), "dd_moments")
+    return out
+
+
+def normalize_advantages(x: torch.Tensor, eps: float = 1e-8, reduce: bool = True,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Globally normalised advantages; ``reduce=True`` sums the moments over all ranks first."""
+    m = advantage_moments(x)
+    if reduce:
+        allreduce_moments(m)
+    if out is None:
+        out = torch.empty_like(x)
+    nv.check(nv.lib().dd_normalize(x.data_ptr(), out.data_ptr(), m.data_ptr(), float(eps), x.numel(), _stream(x)),
+             "dd_normalize")
+    return out
