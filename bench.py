@@ -208,7 +208,7 @@ def run_ours(args):
     # ---- SHARDS independent 1M-env shards per GPU; global env ids are unique over the whole job ----
     envs = [dd.BatchedDroneEnv(n, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
                                max_steps=MAX_STEPS, auto_reset=True, dtype=torch.float32,
-                               env_id_base=(rank * S + s) * n) for s in range(S)]
+                               env_id_base=(rank * S + s) * n, launch_flags=args.launch_flags) for s in range(S)]
     for e in envs:
         e.reset()
     TRACE = 64                                            # steps of pre-generated actions per shard
@@ -320,7 +320,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "envs_per_gpu_per_step": n, "shards_per_gpu": S,
                        "l2": f"inputs larger than L2: steps rotate over {S} independent {n}-env shards "
                              f"({S} x ~{n * 116 >> 20} MiB state+outputs > 126 MB L2)",
-                       "launch": f"CUDA graph of {G} step launches, replayed", "parallelism": f"env-sharded x{ws}, no per-step comms"},
+                       "launch": f"CUDA graph of {G} step launches, replayed; launch_flags={args.launch_flags:#x}", "parallelism": f"env-sharded x{ws}, no per-step comms"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel<float,AUTO,OBS>", "achieved": achieved, "peak": peak_gbs,
                          "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n},
@@ -364,8 +364,10 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per shard (= per step launch)")
     ap.add_argument("--shards", type=int, default=6, help="independent shards per GPU that steps rotate over")
     ap.add_argument("--e2e-steps", type=int, default=300)
-    ap.add_argument("--cpu-ticks", type=int, default=80000)
+    ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch-flags", type=lambda v: int(v, 0), default=0x01,
+                    help="DD_LAUNCH_* bits (include/drone_b200.h): 0x01 PDL, 0x10 CTA 128, 0x20 CTA 512")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

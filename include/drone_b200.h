@@ -50,7 +50,15 @@ extern "C" {
 #define DD_OBS_DIM      15     /* policy input, Actor_Critic_PPO.ipynb c10:L3-19           */
 #define DD_STATS_SLOTS  64     /* contention-spreading copies of the stats block           */
 #define DD_STATS_WORDS  8
+#define DD_MAX_ENVS_PER_CALL 0x7fffff00   /* 32-bit env index inside one call; shard above that */
 #define DD_RETURN_FIXED_SCALE 1048576.0   /* sum_return is accumulated as int64 in units of 2^-20 */
+
+/* ---- DDEnvConfig.launch_flags ------------------------------------------------- */
+#define DD_LAUNCH_PDL        0x01   /* programmatic dependent launch: this kernel's CTAs may become
+                                       resident while the previous kernel of the stream drains; the
+                                       kernel itself waits (griddepcontrol.wait) before its first load */
+#define DD_LAUNCH_BLOCK_128  0x10   /* dd_step CTA size (default 256) */
+#define DD_LAUNCH_BLOCK_512  0x20
 
 /* error codes */
 #define DD_E_NULL    (-1)
@@ -110,6 +118,8 @@ typedef struct DDEnvConfig {
     int32_t auto_reset;      /* 0: freeze after done (game_engine.py:107-111); 1: same-step reset */
     int32_t randomize_drone; /* DroneGame(randomize_drone=...)    game_engine.py:14 */
     int32_t randomize_platform; /* DroneGame(randomize_platform=...) */
+    int32_t launch_flags;    /* DD_LAUNCH_* bits; 0 = plain stream-ordered launch */
+    int32_t reserved;        /* must be 0 */
 } DDEnvConfig;
 
 int  dd_abi_version(void);
@@ -148,8 +158,11 @@ int dd_pack_actions(const uint8_t *actions3, uint8_t *packed, int64_t n, void *s
 
 /* Collapse the DD_STATS_SLOTS copies into out[DD_STATS_WORDS] (device):
  *   0 episodes, 1 landed, 2 crashed, 3 truncated, 4 sum_return (int64, 2^-20 units),
- *   5 sum_length, 6 env_steps, 7 reserved.  (Actor_Critic_PPO.ipynb c21:L94-95,L158-159,L169) */
-int dd_stats_collapse(const uint64_t *stats, uint64_t *out, void *stream);
+ *   5 sum_length (steps of the finished episodes), 6 env_steps = sum_length + the steps so far of
+ *   the episodes still running (needs steps/flags of the n envs; NULL/NULL: finished only),
+ *   7 reserved.  (Actor_Critic_PPO.ipynb c21:L94-95,L158-159,L169) */
+int dd_stats_collapse(const uint64_t *stats, const int32_t *steps, const uint8_t *flags, int64_t n,
+                      uint64_t *out, void *stream);
 
 /* n, sum x, sum x^2 of a float vector into out[3] (device doubles); ACCUMULATES into out.
  * (advantage normalisation moments, Actor_Critic_PPO.ipynb c21:L105) */

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libdrone_b200.so")
 SOURCES = ("drone_kernels.cu", "ppo_kernels.cu", "policy_rollout.cu")
 NVCC_FLAGS = (
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--extended-lambda", "-Xcompiler", "-fPIC", "-shared",
+    "--extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
 )
 
 # ---- constants of include/drone_b200.h ------------------------------------------------------
@@ -30,6 +30,7 @@ POLICY_TRACE, POLICY_RANDOM, POLICY_BANGBANG = 0, 1, 2
 OBS_DIM = 15
 STATS_SLOTS, STATS_WORDS = 64, 8
 RETURN_FIXED_SCALE = 1048576.0
+LAUNCH_PDL, LAUNCH_BLOCK_128, LAUNCH_BLOCK_512 = 0x01, 0x10, 0x20
 
 _PARAM_FIELDS = (
     "width", "height", "gravity", "drag", "angular_drag", "drone_height", "main_thrust", "side_thrust",
@@ -59,6 +60,7 @@ class DDEnvConfig(C.Structure):
         ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
         ("max_steps", C.c_int32), ("auto_reset", C.c_int32),
         ("randomize_drone", C.c_int32), ("randomize_platform", C.c_int32),
+        ("launch_flags", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -128,7 +130,7 @@ def lib():
     L.dd_pack_actions.restype = C.c_int
     L.dd_pack_actions.argtypes = [vp, vp, i64, vp]
     L.dd_stats_collapse.restype = C.c_int
-    L.dd_stats_collapse.argtypes = [vp, vp, vp]
+    L.dd_stats_collapse.argtypes = [vp, vp, vp, i64, vp, vp]
     L.dd_moments.restype = C.c_int
     L.dd_moments.argtypes = [vp, i64, vp, vp]
     L.dd_normalize.restype = C.c_int

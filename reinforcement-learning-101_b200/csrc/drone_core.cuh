@@ -11,6 +11,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <cmath>
 #include "../../include/drone_b200.h"
 
 #if defined(__CUDACC__)
@@ -40,11 +41,18 @@ struct Consts {
     uint32_t spawn_x_count, spawn_y_count, plat_x_count, plat_y_count;
     // reach of the bottom-centre point from the body centre, for the cheap landing pre-test
     R reach_x, reach_y;
+    // speed > land_speed  <=>  vx^2 + vy^2 > speed2_max   (sqrt is correctly rounded and monotonic;
+    // speed2_max = the largest R whose square root rounds to <= land_speed)
+    R speed2_max;
+    // r_step + terminal reward, rounded once in R exactly like the reference's `reward += ...`
+    R rs_land, rs_crash, rs_fuel, rs_oob;
 };
 
+// Everything that is plain arithmetic on DDParams: usable at compile time for the default
+// parameters (the kernels then see immediates instead of constant-bank loads).
 template <typename R>
-inline Consts<R> make_consts(const DDParams& p) {
-    Consts<R> k;
+constexpr Consts<R> make_consts_base(const DDParams& p) {
+    Consts<R> k{};
     k.gravity = (R)p.gravity; k.drag = (R)p.drag; k.ang_drag = (R)p.angular_drag;
     k.main_thrust = (R)p.main_thrust; k.side_thrust = (R)p.side_thrust;
     k.fuel_main = (R)p.fuel_main; k.fuel_side = (R)p.fuel_side; k.max_fuel = (R)p.max_fuel;
@@ -71,6 +79,32 @@ inline Consts<R> make_consts(const DDParams& p) {
     // + 1: slack so that no rounding of (px - x) can reject a state the exact box test accepts
     k.reach_x = (R)(p.platform_w / 2 + p.drone_height / 2 + 1);
     k.reach_y = (R)(p.platform_h / 2 + p.drone_height / 2 + 1);
+    k.speed2_max = (R)((R)p.land_speed * (R)p.land_speed);     // refined by make_consts()
+    k.rs_land = (R)((R)p.r_step + (R)p.r_land); k.rs_crash = (R)((R)p.r_step + (R)p.r_crash);
+    k.rs_fuel = (R)((R)p.r_step + (R)p.r_fuel); k.rs_oob = (R)((R)p.r_step + (R)p.r_oob);
+    return k;
+}
+
+constexpr DDParams kDefaultParams = {
+    800, 600, 0.3, 0.99, 0.95, 20, 0.6, 0.3, 1000.0, 2.0, 1.0, 100, 20, 3.0, 20.0, 50, 50,
+    100.0, -100.0, -50.0, -50.0, -0.1, 500, 5000, 400, 100, 400, 500,
+    100, 601, 50, 201, 100, 600, 100, 450, 10.0, 180.0, 10.0,
+};
+
+// Largest s with fl(sqrt(s)) <= limit, found by walking neighbours of limit^2 (host only).
+template <typename R>
+inline R speed2_threshold(R limit) {
+    R s = limit * limit;
+    const R inf = (R)INFINITY;
+    for (int i = 0; i < 64 && std::sqrt(std::nextafter(s, inf)) <= limit; ++i) s = std::nextafter(s, inf);
+    for (int i = 0; i < 64 && std::sqrt(s) > limit; ++i) s = std::nextafter(s, -inf);
+    return s;
+}
+
+template <typename R>
+inline Consts<R> make_consts(const DDParams& p) {
+    Consts<R> k = make_consts_base<R>(p);
+    k.speed2_max = speed2_threshold<R>((R)p.land_speed);
     return k;
 }
 
@@ -146,9 +180,15 @@ struct Env {
 };
 
 // One DroneGame.step() for a live (not done) environment.  Returns the DD_* flags of this
-// step (0 = still flying) and the engine reward.  `speed` and `dist` come back because the
-// observation wants them too (game_engine.py:166,171).
-template <typename R>
+// step (0 = still flying) and the engine reward.  `dist` (and `speed` when WANT_SPEED) come back
+// because the observation wants them too (game_engine.py:166,171).
+//
+// Written for issue-slot economy (the kernels around it are HBM-bound only if this stays near
+// ~100 instructions): the terminal priority chain is evaluated as selects, not branches; the
+// landing test pays for sin/cos only when the cheap necessary conditions hold (rare); the speed
+// limit is tested on vx^2+vy^2 against a pre-rounded threshold, so the step-only path has a
+// single square root.  Every decision is the reference's, bit for bit, in R arithmetic.
+template <typename R, bool WANT_SPEED>
 DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward, R& speed, R& dist)
 {
     using A = Arith<R>;
@@ -158,7 +198,7 @@ DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward,
     if ((act & DD_ACT_MAIN) && fuel > (R)0) {
         R s, c;
         A::sincos_deg(e.angle, s, c);                      // pre-update angle
-        vx = A::fma_(k.main_thrust, s, vx);                 // 0*c - (-0.6)*s    physics.py:20
+        vx = A::fma_(k.main_thrust, s, vx);                // 0*c - (-0.6)*s    physics.py:20
         vy = A::fma_(-k.main_thrust, c, vy);               // 0*s + (-0.6)*c    physics.py:21
         fuel -= k.fuel_main;
     }
@@ -174,42 +214,42 @@ DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward,
     const R y = A::add(e.y, vy);
     R ang = A::add(e.angle, w);
     w = A::mul(w, k.ang_drag);
-    while (ang > (R)180) ang -= (R)360;                    // physics.py:35-39
-    while (ang < (R)-180) ang += (R)360;
-
+    if (A::abs_(ang) > (R)180) {                           // physics.py:35-39 (rarely taken)
+        while (ang > (R)180) ang -= (R)360;
+        while (ang < (R)-180) ang += (R)360;
+    }
     e.x = x; e.y = y; e.vx = vx; e.vy = vy; e.angle = ang; e.angvel = w; e.fuel = fuel;
 
     // --- terminal tests, game_engine.py:185-216 ----------------------------------------------
-    speed = A::sqrt_(A::fma_(vx, vx, A::mul(vy, vy)));                 // drone.py:145
+    const R speed2 = A::fma_(vx, vx, A::mul(vy, vy));                  // drone.py:145 (before sqrt)
+    if (WANT_SPEED) speed = A::sqrt_(speed2);
     const R ddx = e.px - x, ddy = e.py - y;
     dist = A::sqrt_(A::fma_(ddx, ddx, A::mul(ddy, ddy)));              // physics.py:44
 
+    // Priority (game_engine.py:187-214): landing, ground, fuel, out of bounds, else shaping.
+    // Build it from the lowest priority up with selects.
+    const bool oob = (x < k.x_lo) | (x > k.x_hi) | (y < k.y_lo) | (y > k.y_hi);   // :275-279
+    const bool fuel_out = fuel <= (R)0;                                             // :200-204
+    const bool ground = y > k.ground_y;                                             // :254-265
+    R r = A::add(k.r_step, A::div(k.shape_offset - dist, k.shape_div, k.inv_shape_div));   // :213-214
     uint32_t f = 0;
-    R r = k.r_step;
+    if (oob) { f = DD_DONE | DD_CRASHED | DD_CAUSE_OOB; r = k.rs_oob; }
+    if (fuel_out) { f = DD_DONE | DD_CRASHED | DD_CAUSE_FUEL; r = k.rs_fuel; }
+    if (ground) { f = DD_DONE | DD_CRASHED | DD_CAUSE_GROUND; r = k.rs_crash; }
     // Landing needs all of: bottom centre in the closed platform box, speed <= 3, |angle| <= 20
     // (game_engine.py:224-242).  The bottom centre is at most half_h from the body centre, so
-    // the box test can only pass when |dx| <= w/2 + half_h and |dy| <= h/2 + half_h: test that
-    // (and the two cheap conditions) before paying for sin/cos of the post-update angle.
-    bool landed = false;
-    if (!(speed > k.land_speed) && A::abs_(ang) <= k.land_angle &&
+    // the box test can only pass when |dx| <= w/2 + half_h and |dy| <= h/2 + half_h (+1 slack):
+    // test that and the two cheap conditions before paying for sin/cos of the post-update angle.
+    if (!(speed2 > k.speed2_max) && A::abs_(ang) <= k.land_angle &&
         A::abs_(ddx) <= k.reach_x && A::abs_(ddy) <= k.reach_y) {
         R s, c;
         A::sincos_deg(ang, s, c);
         const R bx = A::fma_(-k.half_h, s, x);             // x + (0*c - 10*s)  drone.py:136-137
         const R by = A::fma_(k.half_h, c, y);              // y + (0*s + 10*c)
-        landed = (e.px - k.plat_half_w <= bx) && (bx <= e.px + k.plat_half_w) &&
-                 (e.py - k.plat_half_h <= by) && (by <= e.py + k.plat_half_h);   // platform.py:74
-    }
-    if (landed) {
-        f = DD_DONE | DD_LANDED; r += k.r_land;
-    } else if (y > k.ground_y) {                           // game_engine.py:254-265
-        f = DD_DONE | DD_CRASHED | DD_CAUSE_GROUND; r += k.r_crash;
-    } else if (fuel <= (R)0) {                             // game_engine.py:200-204
-        f = DD_DONE | DD_CRASHED | DD_CAUSE_FUEL; r += k.r_fuel;
-    } else if (x < k.x_lo || x > k.x_hi || y < k.y_lo || y > k.y_hi) {   // :275-279
-        f = DD_DONE | DD_CRASHED | DD_CAUSE_OOB; r += k.r_oob;
-    } else {
-        r = A::add(r, A::div(k.shape_offset - dist, k.shape_div, k.inv_shape_div));   // :213-214
+        if ((e.px - k.plat_half_w <= bx) && (bx <= e.px + k.plat_half_w) &&
+            (e.py - k.plat_half_h <= by) && (by <= e.py + k.plat_half_h)) {      // platform.py:74
+            f = DD_DONE | DD_LANDED; r = k.rs_land;
+        }
     }
     reward = r;
     e.ret = A::add(e.ret, r);                              // game_engine.py:131

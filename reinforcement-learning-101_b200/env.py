@@ -75,7 +75,7 @@ class BatchedDroneEnv:
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, randomize_drone: bool = False,
                  randomize_platform: bool = True, max_steps: Optional[int] = None, auto_reset: bool = True,
                  dtype: torch.dtype = torch.float32, env_id_base: int = 0, obs_stride: int = nv.OBS_DIM,
-                 want_final_obs: bool = False, params: Optional[nv.DDParams] = None):
+                 want_final_obs: bool = False, params: Optional[nv.DDParams] = None, launch_flags: int = 0):
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be torch.float32 or torch.float64")
         if obs_stride not in (15, 16):
@@ -114,7 +114,8 @@ class BatchedDroneEnv:
                                  self.steps.data_ptr(), self.episode.data_ptr(), self.flags.data_ptr(),
                                  nv.F32 if dtype == torch.float32 else nv.F64)
         self._cfg = nv.DDEnvConfig(int(seed) & (2 ** 64 - 1), int(env_id_base), int(max_steps or 0),
-                                   int(bool(auto_reset)), int(bool(randomize_drone)), int(bool(randomize_platform)))
+                                   int(bool(auto_reset)), int(bool(randomize_drone)), int(bool(randomize_platform)),
+                                   int(launch_flags), 0)
         self._needs_reset = True
 
     # ---- configuration ------------------------------------------------------------------------
@@ -134,6 +135,15 @@ class BatchedDroneEnv:
     def max_steps(self, v: Optional[int]) -> None:
         """Curriculum knob (Actor_Critic_PPO.ipynb c19:L13-17): takes effect on the next step."""
         self._cfg.max_steps = int(v or 0)
+
+    @property
+    def launch_flags(self) -> int:
+        return self._cfg.launch_flags
+
+    @launch_flags.setter
+    def launch_flags(self, v: int) -> None:
+        """``native.LAUNCH_PDL`` etc. (include/drone_b200.h DD_LAUNCH_*)."""
+        self._cfg.launch_flags = int(v)
 
     @property
     def auto_reset(self) -> bool:
@@ -255,8 +265,10 @@ class BatchedDroneEnv:
     # ---- episode statistics (K3) --------------------------------------------------------------------
     def stats_tensor(self) -> torch.Tensor:
         """int64[8] on device: episodes, landed, crashed, truncated, sum_return (2^-20 units),
-        sum_length, env_steps, reserved -- accumulated since the last ``reset_stats()``."""
-        nv.check(self._lib.dd_stats_collapse(self.stats_slots.data_ptr(), self._stats_out.data_ptr(), self._stream()),
+        sum_length, env_steps (= sum_length + steps so far of the running episodes), reserved --
+        accumulated since the last ``reset_stats()``."""
+        nv.check(self._lib.dd_stats_collapse(self.stats_slots.data_ptr(), self.steps.data_ptr(), self.flags.data_ptr(),
+                                             self.num_envs, self._stats_out.data_ptr(), self._stream()),
                  "dd_stats_collapse")
         return self._stats_out
 
