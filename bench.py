@@ -215,9 +215,11 @@ def run_ours(args):
     traces = [e.random_actions(TRACE) for e in envs]
     launches = 0
 
-    def eager_steps(k0: int, k: int, want_obs: bool):
+    def eager_steps(k0: int, k: int, want_obs: bool, only_chain=None):
         for j in range(k0, k0 + k):
             s = j % S
+            if only_chain is not None and s % C_ != only_chain:
+                continue
             envs[s].step_raw(traces[s][(j // S) % TRACE], want_obs=want_obs)
 
     def timed(fn_warm, fn_run):
@@ -233,14 +235,27 @@ def run_ours(args):
     # CUDA graph of G consecutive steps (a whole number of shard rotations) removes the host launch cost
     G = S * max(1, min(TRACE, 96 // S))
 
+    # Shards are independent environments, so their step launches need no mutual ordering: the graph
+    # has C_ parallel chains (shard s on chain s % C_).  Each shard's own steps stay stream-ordered;
+    # kernels of different chains overlap, which hides the fill / drain of one ~15 us launch behind
+    # the next (a single chain leaves ~3 us of pipeline drain between dependent launches).
+    C_ = max(1, min(args.chains, S))
+    chain_streams = [torch.cuda.Stream(dev) for _ in range(C_)]
+
     def make_graph(want_obs: bool):
         g = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(dev)
+        side = chain_streams[0]
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             eager_steps(0, S, want_obs)                   # warm the capture stream
             with torch.cuda.graph(g, stream=side):
-                eager_steps(0, G, want_obs)
+                for c in range(1, C_):                    # fork
+                    chain_streams[c].wait_stream(side)
+                for c in range(C_):
+                    with torch.cuda.stream(chain_streams[c]):
+                        eager_steps(0, G, want_obs, only_chain=c)
+                for c in range(1, C_):                    # join
+                    side.wait_stream(chain_streams[c])
         torch.cuda.current_stream(dev).wait_stream(side)
         return g
 
@@ -320,7 +335,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "envs_per_gpu_per_step": n, "shards_per_gpu": S,
                        "l2": f"inputs larger than L2: steps rotate over {S} independent {n}-env shards "
                              f"({S} x ~{n * 116 >> 20} MiB state+outputs > 126 MB L2)",
-                       "launch": f"CUDA graph of {G} step launches, replayed; launch_flags={args.launch_flags:#x}", "parallelism": f"env-sharded x{ws}, no per-step comms"},
+                       "launch": f"CUDA graph of {G} step launches, replayed, {C_} parallel chain(s) over independent shards; launch_flags={args.launch_flags:#x}", "parallelism": f"env-sharded x{ws}, no per-step comms"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel<float,AUTO,OBS>", "achieved": achieved, "peak": peak_gbs,
                          "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n},
@@ -363,6 +378,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per shard (= per step launch)")
     ap.add_argument("--shards", type=int, default=6, help="independent shards per GPU that steps rotate over")
+    ap.add_argument("--chains", type=int, default=2, help="parallel launch chains in the CUDA graph (shard s -> chain s %% chains)")
     ap.add_argument("--e2e-steps", type=int, default=300)
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
