@@ -185,6 +185,7 @@ def run_ours(args):
     import torch.distributed as dist
     dd = importlib.import_module("reinforcement-learning-101_b200")
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
     rank, local, ws = dd.init_from_env("nccl")
     if ws != args.gpus and ws > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}")

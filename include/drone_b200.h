@@ -175,6 +175,33 @@ int dd_normalize(const float *x, float *y, const double *moments, double eps, in
 int dd_gae(const float *rewards_tn, const float *values_t1n, const uint8_t *dones_tn, float *adv_tn,
            float *returns_tn, double gamma, double lambda, int32_t T, int64_t n, void *stream);
 
+/* ---- K5: fused policy rollout (Actor_Critic_PPO.ipynb c11, c16) ---------------------------- */
+/* fp32 parameters of DroneGamerBoi exactly as torch stores them: nn.Linear.weight is [out][in]
+ * row-major; g / be are nn.LayerNorm weight / bias.  15-128-128-64-3. */
+typedef struct DDPolicy {
+    const float *w0, *b0, *g0, *be0;      /* network.0 (Linear 15->128), network.1 (LayerNorm 128) */
+    const float *w1, *b1, *g1, *be1;      /* network.3 (Linear 128->128), network.4 */
+    const float *w2, *b2, *g2, *be2;      /* network.6 (Linear 128->64), network.7 */
+    const float *w3, *b3;                 /* network.9 (Linear 64->3) */
+} DDPolicy;
+
+#define DD_POLICY_BLOB_BYTES 57360        /* device workspace filled by dd_policy_pack */
+#define DD_ACTION_THRESHOLD 0             /* action = probs > 0.5        (c18:L24-25) */
+#define DD_ACTION_SAMPLE    1             /* action ~ Bernoulli(probs)   (c16:L61-63), Philox */
+
+/* fp32 torch parameters -> bf16 tensor-core operand images + fp32 LN parameters (16-byte aligned blob). */
+int dd_policy_pack(const DDPolicy *p, void *blob, void *stream);
+
+/* probs[n][3] = policy(obs[n][15]) through the same tcgen05 path the rollout uses (parity hook). */
+int dd_policy_forward(const void *blob, const float *obs, float *probs, int64_t n, void *stream);
+
+/* T steps of {observe, policy, act, step} in one launch; DD_F32 state only.  Optional [T][n] outputs:
+ * actions (DD_ACT_* bits), logp (sum of the 3 Bernoulli log-probs), reward, done flags, obs [T][n][15],
+ * probs [T][n][3]. */
+int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, const void *blob, int32_t mode,
+                      uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
+                      uint8_t *done_tn, float *obs_tn, float *probs_tn, uint64_t *stats, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

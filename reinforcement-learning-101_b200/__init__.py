@@ -16,7 +16,7 @@ from .distributed import (allreduce_moments, allreduce_stats, init_from_env, mea
 
 __all__ = ["native", "build_native", "BatchedDroneEnv", "StepInfo", "gae", "advantage_moments",
            "normalize_advantages", "allreduce_stats", "allreduce_moments", "shard_range", "stats_dict",
-           "mean_std_from_moments", "init_from_env"]
+           "mean_std_from_moments", "init_from_env", "PolicyBlob", "policy_forward", "policy_rollout"]
 
 
 def __getattr__(name):
@@ -28,6 +28,9 @@ def __getattr__(name):
     if name in ("gae", "advantage_moments", "normalize_advantages"):
         from . import ppo_ops
         return getattr(ppo_ops, name)
+    if name in ("PolicyBlob", "policy_forward", "policy_rollout"):
+        from . import policy
+        return getattr(policy, name)
     if name in ("compat", "env", "ppo_ops", "policy"):
         import importlib
         return importlib.import_module("." + name, __name__)

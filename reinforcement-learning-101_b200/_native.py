@@ -137,10 +137,12 @@ def lib():
     L.dd_normalize.argtypes = [vp, vp, vp, C.c_double, i64, vp]
     L.dd_gae.restype = C.c_int
     L.dd_gae.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp]
-    if hasattr(L, "dd_policy_rollout"):
-        L.dd_policy_rollout.restype = C.c_int
-        L.dd_policy_rollout.argtypes = [PS, PP, PC, C.POINTER(DDPolicy), i32, u32, i32,
-                                        vp, vp, vp, vp, vp, vp, i64, vp]
+    L.dd_policy_pack.restype = C.c_int
+    L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, vp]
+    L.dd_policy_forward.restype = C.c_int
+    L.dd_policy_forward.argtypes = [vp, vp, vp, i64, vp]
+    L.dd_policy_rollout.restype = C.c_int
+    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     if L.dd_abi_version() != ABI_VERSION:
         raise NativeError(f"libdrone_b200.so ABI {L.dd_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L
@@ -162,4 +164,5 @@ def default_params() -> DDParams:
 EXPORTS = (
     "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
+    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout",
 )

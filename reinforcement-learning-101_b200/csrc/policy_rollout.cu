@@ -1,0 +1,485 @@
+// policy_rollout.cu -- K5: the PPO rollout inner loop fused into ONE persistent kernel.
+//
+// Replaces `collect_episodes_ppo`'s per-step work (Actor_Critic_PPO.ipynb c16:L42-108): stack the
+// observations, run the policy `DroneGamerBoi` (c11:L5-17: Linear(15,128)-LN-ReLU-Linear(128,128)-LN-
+// ReLU-Linear(128,64)-LN-ReLU-Linear(64,3)-Sigmoid), sample 3 independent Bernoulli actions
+// (c16:L61-63) or threshold them (c18:L24-25), step every game, append to the rollout buffers.
+//
+// Mapping to sm_100a:
+//   * one CTA per SM, 512 threads = 4 warpgroup "tiles" of 128 environments; a thread owns ONE
+//     environment for the whole T-step rollout (state in registers) and the matching accumulator
+//     row (TMEM lane) of its tile;
+//   * the three dense layers run on the 5th-gen tensor cores: `tcgen05.mma.cta_group::1.kind::f16`
+//     (SASS UTCHMMA), M = 128 (envs) x N = 128/128/64 x K = 16/128/128, bf16 operands from shared
+//     memory (UMMA K-major, no-swizzle canonical layout), fp32 accumulators in TMEM (128 columns
+//     per tile, 512 = the whole TMEM per CTA), issued by one elected thread per tile and tracked with
+//     `tcgen05.commit` -> mbarrier;
+//   * LayerNorm + ReLU + the bf16 re-quantisation of the next layer's A operand are the epilogue:
+//     each thread reads its accumulator row with `tcgen05.ld.32x32b.x32` (SASS LDTM), twice (moments,
+//     then normalise), and writes the next A tile straight into the UMMA layout;
+//   * weights (bf16, already in UMMA layout) + LN parameters live in shared memory for the whole
+//     kernel (57 KB), the A tiles take 32 KB per tile: 185 KB of the 227 KB;
+//   * the last layer (64 -> 3) and the sigmoid / Bernoulli / log-prob are folded into the third
+//     epilogue on the CUDA cores; the environment step is `step_core` from drone_core.cuh, the
+//     same code as K1, so the environment side is bit-identical to dd_rollout on the same actions.
+// The four tiles of a CTA are independent pipelines, so while one waits for its MMAs the other three
+// keep the CUDA cores busy: this kernel is bound by the epilogue arithmetic (~2.5 k instructions per
+// env-step), not by the tensor pipe.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string.h>
+#include "drone_device.cuh"
+
+namespace dd {
+
+constexpr int kTile = 128;                     // envs per tile == UMMA M == TMEM lanes
+constexpr int kGroups = 4;                     // tiles per CTA
+constexpr int kPolThreads = kTile * kGroups;   // 512
+constexpr int kH1 = 128, kH2 = 128, kH3 = 64, kIn = 15, kInPad = 16, kOut = 3;
+
+// ---- parameter blob (device memory, produced by policy_pack_kernel; copied verbatim to smem) ----
+// bf16 weight images in UMMA K-major no-swizzle layout: element (n, k) of a [N][K] matrix sits at
+// byte (k / 8) * (N * 16) + n * 16 + (k % 8) * 2   (8x16-byte core matrices; LBO = N*16, SBO = 128)
+constexpr int kW0Off = 0;                                  // [128][16]  (col 15 = bias b0: obs[15] := 1)
+constexpr int kW1Off = kW0Off + kH1 * kInPad * 2;          // [128][128]
+constexpr int kW2Off = kW1Off + kH2 * kH1 * 2;             // [64][128]
+constexpr int kParOff = kW2Off + kH3 * kH2 * 2;            // fp32 parameters
+// fp32 parameter order
+constexpr int pG0 = 0, pBe0 = 128, pB1 = 256, pG1 = 384, pBe1 = 512, pB2 = 640, pG2 = 704, pBe2 = 768,
+              pW3 = 832, pB3 = 1024, kParFloats = 1028;
+constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 57,360
+static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
+static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
+
+constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
+constexpr int kSmemBlob = 0;
+constexpr int kSmemA = ((kBlobBytes + 1023) / 1024) * 1024;
+constexpr int kSmemBar = kSmemA + kGroups * kABytes;
+constexpr int kSmemTotal = kSmemBar + 64;
+
+struct PArgs {
+    KArgs<float> a;        // env state pointers etc.
+    const uint8_t* blob;
+    int32_t mode;              // DD_SAMPLE_*
+    uint32_t t0;
+    int32_t T;
+    uint8_t* actions_tn;
+    float* logp_tn;
+    float* reward_tn;
+    uint8_t* done_tn;
+    float* obs_tn;             // [T][n][15]
+    float* probs_tn;           // [T][n][3] (optional)
+    const float* obs_in;       // forward-only mode: [n][15], no env stepping
+    int32_t auto_reset;
+};
+
+// ---- raw PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();        // a lost MMA completion must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "n"(kTile) : "memory"); }
+
+// UMMA shared-memory matrix descriptor: K-major, no swizzle, 8x16-byte core matrices.
+//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (next 16-byte K chunk)
+//   | [32,46) stride byte offset >> 4 (next 8-row group) | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::f16: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);    // .x = lo (low 16 bits)
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+// ---- one hidden layer's epilogue: bias + LayerNorm + ReLU over N columns of my accumulator row -----
+// Pass 1 reads the row for the moments, pass 2 re-reads it and calls sink(chunk, y[32]).
+template <int N, typename Sink>
+__device__ __forceinline__ void ln_relu_epilogue(uint32_t trow, const float* __restrict__ bias,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta, Sink sink)
+{
+    float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+        float v[32];
+        tmem_ld32(trow + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = bias ? v[j] + bias[c * 32 + j] : v[j];
+            sum += x;
+            sq = fmaf(x, x, sq);
+        }
+    }
+    const float mean = sum * (1.0f / N);
+    const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / N)), 0.f);      // biased, like nn.LayerNorm
+    const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+        float v[32];
+        tmem_ld32(trow + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = bias ? v[j] + bias[c * 32 + j] : v[j];
+            const float y = fmaf((x - mean) * rstd, gamma[c * 32 + j], beta[c * 32 + j]);
+            v[j] = fmaxf(y, 0.f);
+        }
+        sink(c, v);
+    }
+}
+
+// write 32 activations of my row (K columns 32c..32c+31) as bf16 into the A tile (UMMA layout)
+__device__ __forceinline__ void store_a_chunk32(uint8_t* a_tile, int row, int c, const float (&y)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                           // four 16-byte K chunks
+        uint4 w;
+        w.x = pack_bf16(y[8 * q + 0], y[8 * q + 1]); w.y = pack_bf16(y[8 * q + 2], y[8 * q + 3]);
+        w.z = pack_bf16(y[8 * q + 4], y[8 * q + 5]); w.w = pack_bf16(y[8 * q + 6], y[8 * q + 7]);
+        *reinterpret_cast<uint4*>(a_tile + (4 * c + q) * (kTile * 16) + row * 16) = w;
+    }
+}
+
+// =================================================================================================
+template <bool DEF>
+__global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const KArgs<float>& a = pa.a;
+    const Consts<float> k = consts_of<float, DEF>(a);
+
+    const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, row = tid & (kTile - 1);
+    uint8_t* s_blob = smem + kSmemBlob;
+    uint8_t* s_a = smem + kSmemA + g * kABytes;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);          // [kGroups]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 40);
+    const float* s_par = reinterpret_cast<const float*>(s_blob + kParOff);
+
+    // ---- one-time setup: weights -> smem, mbarriers, TMEM ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(pa.blob);
+        uint4* dst = reinterpret_cast<uint4*>(s_blob);
+        for (int j = tid; j < kBlobBytes / 16; j += kPolThreads) dst[j] = __ldg(src + j);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) mbar_init(smem_u32(s_bar + j), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {                                        // one warp allocates the whole TMEM (512 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();                                     // weight image (generic stores) -> async proxy (UMMA reads)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_d = tmem_base + (uint32_t)(g * 128);                         // my tile's accumulator columns
+    const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);              // my warp's 32 lanes
+    const uint32_t bar = smem_u32(s_bar + g);
+    const uint32_t a_addr = smem_u32(s_a);
+    const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
+    uint32_t phase = 0;
+
+    // ---- my environment ----
+    const uint32_t tile0 = (blockIdx.x * kGroups + g) * kTile;
+    const uint32_t i = tile0 + row;
+    const bool live = i < a.n;
+    const bool forward_only = pa.obs_in != nullptr;
+    Env<float> e = {};
+    uint32_t pflags = 0, ep = 0;
+    bool platform_dirty = false;
+    if (live && !forward_only) {
+        load4(a.pos_vel, i, e.x, e.y, e.vx, e.vy);
+        load4(a.att_fuel, i, e.angle, e.angvel, e.fuel, e.ret);
+        load2(a.platform, i, e.px, e.py);
+        e.steps = a.steps[i];
+        pflags = a.flags[i];
+        ep = a.episode[i];
+    }
+    const uint64_t gid = a.env_id_base + (uint64_t)i;
+    float speed = 0.f, dist = 0.f;
+    if (!forward_only) speed_dist(e, speed, dist);
+
+    for (int32_t t = 0; t < pa.T; ++t) {
+        const size_t o = (size_t)t * a.n + i;
+        // ---------------- observation -> A0 (bf16, K = 16: 15 inputs + constant 1 for the bias) -------
+        float ob[16];
+        if (forward_only) {
+#pragma unroll
+            for (int j = 0; j < kIn; ++j) ob[j] = live ? pa.obs_in[(size_t)i * kIn + j] : 0.f;
+        } else {
+            write_obs(e, pflags, speed, dist, k, [&](int j, float v) { ob[j] = v; });
+            if (pa.obs_tn && live) {
+                float* dst = pa.obs_tn + o * kIn;
+#pragma unroll
+                for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
+            }
+        }
+        ob[15] = 1.0f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint4 w;
+            w.x = pack_bf16(ob[8 * q + 0], ob[8 * q + 1]); w.y = pack_bf16(ob[8 * q + 2], ob[8 * q + 3]);
+            w.z = pack_bf16(ob[8 * q + 4], ob[8 * q + 5]); w.w = pack_bf16(ob[8 * q + 6], ob[8 * q + 7]);
+            *reinterpret_cast<uint4*>(s_a + q * (kTile * 16) + row * 16) = w;
+        }
+        // ---------------- layer 1: D[128x128] = A0[128x16] * W0^T -------------------------------------
+        fence_async_smem(); tc_fence_before(); group_bar(g);
+        if (row == 0) {
+            tc_fence_after();
+            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
+        ln_relu_epilogue<kH1>(trow, nullptr, s_par + pG0, s_par + pBe0,
+                              [&](int c, const float (&y)[32]) { store_a_chunk32(s_a, row, c, y); });
+        // ---------------- layer 2: D[128x128] = A1[128x128] * W1^T ------------------------------------
+        fence_async_smem(); tc_fence_before(); group_bar(g);
+        if (row == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kH1 / 16; ++j)
+                umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
+                          umma_desc(w1_addr + j * 2 * (kH2 * 16), kH2 * 16, 128), umma_idesc(128, kH2), j > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
+        ln_relu_epilogue<kH2>(trow, s_par + pB1, s_par + pG1, s_par + pBe1,
+                              [&](int c, const float (&y)[32]) { store_a_chunk32(s_a, row, c, y); });
+        // ---------------- layer 3: D[128x64] = A2[128x128] * W2^T -------------------------------------
+        fence_async_smem(); tc_fence_before(); group_bar(g);
+        if (row == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kH2 / 16; ++j)
+                umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
+                          umma_desc(w2_addr + j * 2 * (kH3 * 16), kH3 * 16, 128), umma_idesc(128, kH3), j > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
+        // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
+        float z0 = s_par[pB3 + 0], z1 = s_par[pB3 + 1], z2 = s_par[pB3 + 2];
+        ln_relu_epilogue<kH3>(trow, s_par + pB2, s_par + pG2, s_par + pBe2, [&](int c, const float (&y)[32]) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                z0 = fmaf(y[j], s_par[pW3 + 0 * kH3 + c * 32 + j], z0);
+                z1 = fmaf(y[j], s_par[pW3 + 1 * kH3 + c * 32 + j], z1);
+                z2 = fmaf(y[j], s_par[pW3 + 2 * kH3 + c * 32 + j], z2);
+            }
+        });
+        tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
+        const float p0 = 1.0f / (1.0f + __expf(-z0)), p1 = 1.0f / (1.0f + __expf(-z1)), p2 = 1.0f / (1.0f + __expf(-z2));
+        if (pa.probs_tn && live) {
+            float* dst = pa.probs_tn + o * kOut;
+            dst[0] = p0; dst[1] = p1; dst[2] = p2;
+        }
+        if (forward_only) continue;
+
+        // ---------------- action: threshold (c18:L24-25) or Bernoulli sample (c16:L61-63) --------------
+        uint32_t act;
+        float logp = 0.f;
+        if (pa.mode == DD_ACTION_THRESHOLD) {
+            act = (p0 > 0.5f ? DD_ACT_MAIN : 0u) | (p1 > 0.5f ? DD_ACT_LEFT : 0u) | (p2 > 0.5f ? DD_ACT_RIGHT : 0u);
+        } else {
+            const U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
+                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            const float u0 = (float)(r.a >> 8) * (1.0f / 16777216.0f), u1 = (float)(r.b >> 8) * (1.0f / 16777216.0f),
+                        u2 = (float)(r.c >> 8) * (1.0f / 16777216.0f);
+            act = (u0 < p0 ? DD_ACT_MAIN : 0u) | (u1 < p1 ? DD_ACT_LEFT : 0u) | (u2 < p2 ? DD_ACT_RIGHT : 0u);
+        }
+        if (pa.logp_tn) {                                    // Bernoulli(probs).log_prob(a).sum(), probs clamped like torch
+            const float eps = 1.1920929e-07f;
+            const float q0 = fminf(fmaxf(p0, eps), 1.f - eps), q1 = fminf(fmaxf(p1, eps), 1.f - eps), q2 = fminf(fmaxf(p2, eps), 1.f - eps);
+            logp = __logf((act & DD_ACT_MAIN) ? q0 : 1.f - q0) + __logf((act & DD_ACT_LEFT) ? q1 : 1.f - q1) +
+                   __logf((act & DD_ACT_RIGHT) ? q2 : 1.f - q2);
+        }
+
+        // ---------------- environment step (same code as K1) -------------------------------------------
+        uint32_t oflags = pflags, f_stat = 0;
+        double ret_stat = 0.0; int32_t len_stat = 0;
+        float reward = 0.f;
+        if (live) {
+            if (!(pflags & DD_DONE)) {
+                uint32_t f = step_core<float, true>(e, act, k, reward, speed, dist);
+                if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
+                oflags = f;
+                if (f) {
+                    f_stat = f; ret_stat = (double)e.ret; len_stat = e.steps;
+                    if (pa.auto_reset) {
+                        spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
+                        ep += 1;
+                        platform_dirty = true;
+                        f = 0;
+                        speed_dist(e, speed, dist);
+                    }
+                }
+                pflags = f;
+            }
+            if (pa.actions_tn) pa.actions_tn[o] = (uint8_t)act;
+            if (pa.logp_tn) pa.logp_tn[o] = logp;
+            if (pa.reward_tn) pa.reward_tn[o] = reward;
+            if (pa.done_tn) pa.done_tn[o] = (uint8_t)oflags;
+        }
+        if (a.stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
+    }
+
+    if (live && !forward_only) {
+        store4(a.pos_vel, i, e.x, e.y, e.vx, e.vy);
+        store4(a.att_fuel, i, e.angle, e.angvel, e.fuel, e.ret);
+        a.steps[i] = e.steps;
+        a.flags[i] = (uint8_t)pflags;
+        a.episode[i] = ep;
+        if (platform_dirty) store2(a.platform, i, e.px, e.py);
+    }
+    // ---- teardown: everyone is done with TMEM, then the allocating warp frees it ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- fp32 torch parameters -> blob ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, uint8_t* blob)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(blob + kW0Off);
+    __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(blob + kW1Off);
+    __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(blob + kW2Off);
+    float* par = reinterpret_cast<float*>(blob + kParOff);
+    auto at = [](int N, int n, int kk) { return (kk / 8) * (N * 8) + n * 8 + (kk % 8); };   // element index in the image
+    for (int j = tid; j < kH1 * kInPad; j += nth) {
+        const int n = j / kInPad, kk = j % kInPad;
+        w0[at(kH1, n, kk)] = __float2bfloat16_rn(kk < kIn ? p.w0[n * kIn + kk] : p.b0[n]);
+    }
+    for (int j = tid; j < kH2 * kH1; j += nth) { const int n = j / kH1, kk = j % kH1; w1[at(kH2, n, kk)] = __float2bfloat16_rn(p.w1[j]); }
+    for (int j = tid; j < kH3 * kH2; j += nth) { const int n = j / kH2, kk = j % kH2; w2[at(kH3, n, kk)] = __float2bfloat16_rn(p.w2[j]); }
+    for (int j = tid; j < 128; j += nth) {
+        par[pG0 + j] = p.g0[j]; par[pBe0 + j] = p.be0[j];
+        par[pB1 + j] = p.b1[j]; par[pG1 + j] = p.g1[j]; par[pBe1 + j] = p.be1[j];
+    }
+    for (int j = tid; j < 64; j += nth) { par[pB2 + j] = p.b2[j]; par[pG2 + j] = p.g2[j]; par[pBe2 + j] = p.be2[j]; }
+    for (int j = tid; j < kOut * kH3; j += nth) par[pW3 + j] = p.w3[j];
+    for (int j = tid; j < 4; j += nth) par[pB3 + j] = j < kOut ? p.b3[j] : 0.f;
+}
+
+static bool pol_params_default(const DDParams& p)
+{
+    const DDParams d = kDefaultParams;
+    return memcmp(&p, &d, sizeof d) == 0;
+}
+
+static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, cudaStream_t st)
+{
+    const int grid = (int)((n + kTile * kGroups - 1) / (kTile * kGroups));
+    const bool def = pol_params_default(p);
+    auto kern = def ? policy_rollout_kernel<true> : policy_rollout_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (err != cudaSuccess) return (int)err;
+    kern<<<grid, kPolThreads, kSmemTotal, st>>>(pa);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dd
+
+extern "C" {
+
+int dd_policy_pack(const DDPolicy* p, void* blob, void* stream)
+{
+    if (!p || !blob) return DD_E_NULL;
+    const float* const* q = reinterpret_cast<const float* const*>(p);
+    for (int j = 0; j < 14; ++j) if (!q[j]) return DD_E_NULL;
+    if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
+    dd::policy_pack_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(*p, (uint8_t*)blob);
+    return (int)cudaGetLastError();
+}
+
+int dd_policy_forward(const void* blob, const float* obs, float* probs, int64_t n, void* stream)
+{
+    if (!blob || !obs || !probs) return DD_E_NULL;
+    if (n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
+    if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
+    if (n == 0) return 0;
+    dd::PArgs pa{};
+    pa.a.n = (uint32_t)n;
+    pa.blob = (const uint8_t*)blob; pa.T = 1; pa.obs_in = obs; pa.probs_tn = probs;
+    DDParams p = dd::kDefaultParams;
+    return dd::policy_launch(pa, p, n, (cudaStream_t)stream);
+}
+
+int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob, int32_t mode,
+                      uint32_t t0, int32_t T, uint8_t* actions_tn, float* logp_tn, float* reward_tn, uint8_t* done_tn,
+                      float* obs_tn, float* probs_tn, uint64_t* stats, int64_t n, void* stream)
+{
+    if (!s || !p || !c || !blob) return DD_E_NULL;
+    if (s->dtype != DD_F32) return DD_E_DTYPE;                 // the fused kernel is the fp32 throughput path
+    if (mode != DD_ACTION_THRESHOLD && mode != DD_ACTION_SAMPLE) return DD_E_RANGE;
+    if (T < 0 || n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
+    if (n > 0 && (!s->pos_vel || !s->att_fuel || !s->platform || !s->steps || !s->episode || !s->flags)) return DD_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(s->pos_vel) | reinterpret_cast<uintptr_t>(s->att_fuel) | reinterpret_cast<uintptr_t>(blob)) & 15u) return DD_E_ALIGN;
+    if (reinterpret_cast<uintptr_t>(s->platform) & 7u) return DD_E_ALIGN;
+    if (n == 0 || T == 0) return 0;
+    dd::PArgs pa{};
+    pa.a.pos_vel = (float*)s->pos_vel; pa.a.att_fuel = (float*)s->att_fuel; pa.a.platform = (float*)s->platform;
+    pa.a.steps = s->steps; pa.a.episode = s->episode; pa.a.flags = s->flags;
+    pa.a.stats = (unsigned long long*)stats;
+    pa.a.n = (uint32_t)n; pa.a.seed = c->seed; pa.a.env_id_base = c->env_id_base; pa.a.max_steps = c->max_steps;
+    pa.a.rand_drone = c->randomize_drone; pa.a.rand_platform = c->randomize_platform;
+    pa.a.k = dd::make_consts<float>(*p);
+    pa.blob = (const uint8_t*)blob; pa.mode = mode; pa.t0 = t0; pa.T = T;
+    pa.actions_tn = actions_tn; pa.logp_tn = logp_tn; pa.reward_tn = reward_tn; pa.done_tn = done_tn;
+    pa.obs_tn = obs_tn; pa.probs_tn = probs_tn; pa.obs_in = nullptr; pa.auto_reset = c->auto_reset;
+    return dd::policy_launch(pa, *p, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

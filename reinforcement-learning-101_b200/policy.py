@@ -1,0 +1,107 @@
+"""K5 host side: the fused policy rollout (``csrc/policy_rollout.cu``).
+
+``PolicyBlob`` packs the fp32 parameters of the notebook's policy network ``DroneGamerBoi``
+(Actor_Critic_PPO.ipynb c11:L5-17 -- ``nn.Sequential`` indices 0/3/6/9 are the Linears, 1/4/7 the
+LayerNorms) into the bf16 tensor-core operand images the kernel keeps in shared memory.
+``policy_forward`` runs just the network (parity hook against eager torch); ``policy_rollout``
+runs T steps of {observe, policy, act, step} in one launch on a ``BatchedDroneEnv`` and fills
+on-device rollout buffers (obs, action, log-prob, reward, done -- what ``collect_episodes_ppo``,
+c16:L42-108, appends per step).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import _native as nv
+from .env import BatchedDroneEnv
+
+BLOB_BYTES = 57360
+ACTION_THRESHOLD, ACTION_SAMPLE = 0, 1
+_KEYS = ("network.0.weight", "network.0.bias", "network.1.weight", "network.1.bias",
+         "network.3.weight", "network.3.bias", "network.4.weight", "network.4.bias",
+         "network.6.weight", "network.6.bias", "network.7.weight", "network.7.bias",
+         "network.9.weight", "network.9.bias")
+_SHAPES = ((128, 15), (128,), (128,), (128,), (128, 128), (128,), (128,), (128,),
+           (64, 128), (64,), (64,), (64,), (3, 64), (3,))
+
+
+class PolicyBlob:
+    """Device-resident packed policy (57,360 bytes)."""
+
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("PolicyBlob lives on a CUDA device")
+        params = []
+        for key, shape in zip(_KEYS, _SHAPES):
+            if key not in state_dict:
+                raise KeyError(f"state_dict lacks {key!r} (expected the DroneGamerBoi layout)")
+            t = state_dict[key].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{key}: shape {tuple(t.shape)} != {shape}")
+            params.append(t)
+        self._params = params                              # keep alive until the pack kernel has run
+        self.blob = torch.empty(BLOB_BYTES, dtype=torch.uint8, device=self.device)
+        pol = nv.DDPolicy(*[t.data_ptr() for t in params])
+        nv.check(nv.lib().dd_policy_pack(C.byref(pol), self.blob.data_ptr(),
+                                         torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack")
+
+    @classmethod
+    def from_module(cls, module: torch.nn.Module, device="cuda") -> "PolicyBlob":
+        return cls(module.state_dict(), device=device)
+
+
+def policy_forward(blob: PolicyBlob, obs: torch.Tensor) -> torch.Tensor:
+    """probs [N,3] = sigmoid(policy(obs [N,15])) on the tensor-core path."""
+    if not obs.is_cuda or obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[1] != 15:
+        raise ValueError("obs must be a CUDA float32 tensor of shape [N, 15]")
+    obs = obs.contiguous()
+    probs = torch.empty(obs.shape[0], 3, dtype=torch.float32, device=obs.device)
+    nv.check(nv.lib().dd_policy_forward(blob.blob.data_ptr(), obs.data_ptr(), probs.data_ptr(), obs.shape[0],
+                                        torch.cuda.current_stream(obs.device).cuda_stream), "dd_policy_forward")
+    return probs
+
+
+def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool = True, t0: int = 0,
+                   want: str = "arld", out: Optional[Dict[str, torch.Tensor]] = None, stats: bool = True
+                   ) -> Dict[str, torch.Tensor]:
+    """T fused steps on ``env`` (float32 envs only).  ``want`` picks the [T,N] buffers to fill:
+    a=actions (uint8 DD_ACT bits), l=logp, r=reward, d=done flags, o=obs [T,N,15], p=probs [T,N,3].
+    Returns the dict of buffers (allocated unless passed in ``out``)."""
+    if env.dtype != torch.float32:
+        raise ValueError("policy_rollout needs a float32 env")
+    if env._needs_reset:
+        raise RuntimeError("call reset() before policy_rollout()")
+    n, dev = env.num_envs, env.device
+    spec = {"a": ("actions", (T, n), torch.uint8), "l": ("logp", (T, n), torch.float32),
+            "r": ("reward", (T, n), torch.float32), "d": ("done", (T, n), torch.uint8),
+            "o": ("obs", (T, n, 15), torch.float32), "p": ("probs", (T, n, 3), torch.float32)}
+    bufs: Dict[str, torch.Tensor] = dict(out or {})
+    for ch in want:
+        name, shape, dtype = spec[ch]
+        if name not in bufs:
+            bufs[name] = torch.empty(shape, dtype=dtype, device=dev)
+        b = bufs[name]
+        if tuple(b.shape) != shape or b.dtype != dtype or not b.is_contiguous() or b.device != dev:
+            raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {shape} on {dev}")
+    ptr = lambda k: bufs[k].data_ptr() if k in bufs else None
+    nv.check(nv.lib().dd_policy_rollout(
+        C.byref(env._state), C.byref(env.params), C.byref(env._cfg), blob.blob.data_ptr(),
+        ACTION_SAMPLE if sample else ACTION_THRESHOLD, int(t0), int(T), ptr("actions"), ptr("logp"), ptr("reward"),
+        ptr("done"), ptr("obs"), ptr("probs"), env.stats_slots.data_ptr() if stats else None, n, env._stream()),
+        "dd_policy_rollout")
+    return bufs
+
+
+def reference_policy(state_dict: Mapping[str, torch.Tensor]) -> torch.nn.Module:
+    """An eager fp32 torch module with the notebook's architecture (for tests / comparisons)."""
+    net = torch.nn.Sequential(
+        torch.nn.Linear(15, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
+        torch.nn.Linear(128, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
+        torch.nn.Linear(128, 64), torch.nn.LayerNorm(64), torch.nn.ReLU(),
+        torch.nn.Linear(64, 3), torch.nn.Sigmoid())
+    net.load_state_dict({k.replace("network.", ""): v for k, v in state_dict.items()})
+    return net

@@ -1,0 +1,162 @@
+"""K5 -- the fused policy rollout (tcgen05 MLP + env step in one kernel) on the GPU.
+
+Tolerances.  The three dense layers run with bf16 operands and fp32 accumulation, so against the
+notebook's eager fp32 network the logits differ by up to ~6e-2 (measured 0.063 max on the fixture
+batch by a bf16-operand emulation in torch): probabilities are compared with atol 3e-2, and
+thresholded actions may only differ where the fp32 |logit| < 0.15.  Against the bf16-operand
+emulation (same roundings, different summation order) the kernel must agree to 3e-3 -- that is
+the check that the UMMA descriptors / layouts / LayerNorm epilogues are right.
+The environment half is exact: replaying the actions the fused kernel chose through dd_rollout
+must reproduce rewards, flags and final state bit for bit.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+dd = importlib.import_module("reinforcement-learning-101_b200")
+pol = importlib.import_module("reinforcement-learning-101_b200.policy")
+nv = dd.native
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def fixture(golden_dir):
+    d = np.load(os.path.join(golden_dir, "policy_v1.npz"))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files if k.startswith("network")}
+    return d, sd
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _emulate_bf16(sd, x):
+    """Same operand roundings as the kernel: bf16 inputs / weights / hidden activations (and b0, which
+    rides in the bf16 weight image), fp32 accumulation, fp32 LayerNorm, fp32 last layer."""
+    F = torch.nn.functional
+    h = _bf(x) @ _bf(sd["network.0.weight"]).T + _bf(sd["network.0.bias"])
+    h = torch.relu(F.layer_norm(h, (128,), sd["network.1.weight"], sd["network.1.bias"], 1e-5))
+    h = _bf(h) @ _bf(sd["network.3.weight"]).T + sd["network.3.bias"]
+    h = torch.relu(F.layer_norm(h, (128,), sd["network.4.weight"], sd["network.4.bias"], 1e-5))
+    h = _bf(h) @ _bf(sd["network.6.weight"]).T + sd["network.6.bias"]
+    h = torch.relu(F.layer_norm(h, (64,), sd["network.7.weight"], sd["network.7.bias"], 1e-5))
+    return torch.sigmoid(h @ sd["network.9.weight"].T + sd["network.9.bias"])
+
+
+def test_forward_matches_torch_on_the_reference_checkpoint(fixture):
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    obs = torch.from_numpy(d["obs"]).to(DEV)
+    probs = dd.policy_forward(blob, obs).cpu()
+    emu = _emulate_bf16(sd, torch.from_numpy(d["obs"]))
+    ref = torch.from_numpy(d["probs"])
+    assert torch.isfinite(probs).all()
+    assert (probs - emu).abs().max().item() < 3e-3, (probs - emu).abs().max().item()
+    assert (probs - ref).abs().max().item() < 3e-2
+    flips = (probs > 0.5) != (ref > 0.5)
+    assert np.abs(d["logits"])[flips.numpy()].max(initial=0.0) < 0.15
+    # the module-based constructor gives the same blob
+    blob2 = dd.PolicyBlob.from_module(pol.reference_policy(sd), device=DEV)
+    assert torch.equal(blob.blob, blob2.blob)
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 512, 1000])
+def test_forward_random_weights_ragged_sizes(n):
+    g = torch.Generator().manual_seed(n)
+    net = torch.nn.Sequential(
+        torch.nn.Linear(15, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
+        torch.nn.Linear(128, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
+        torch.nn.Linear(128, 64), torch.nn.LayerNorm(64), torch.nn.ReLU(),
+        torch.nn.Linear(64, 3), torch.nn.Sigmoid())
+    with torch.no_grad():
+        for p in net.parameters():                      # non-trivial LN affine and biases
+            p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() > 1 else 0.5) + (1.0 if p.dim() == 1 else 0.0) * 0.5)
+    sd = {"network." + k: v for k, v in net.state_dict().items()}
+    blob = dd.PolicyBlob(sd, device=DEV)
+    x = torch.randn(n, 15, generator=g)
+    probs = dd.policy_forward(blob, x.to(DEV)).cpu()
+    emu = _emulate_bf16(sd, x)
+    assert probs.shape == (n, 3)
+    assert (probs - emu).abs().max().item() < 5e-3, (probs - emu).abs().max().item()
+    with torch.no_grad():
+        assert (probs - net(x)).abs().max().item() < 8e-2
+
+
+def test_rollout_env_half_is_exact_and_buffers_are_consistent(fixture):
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    n, T = 1000, 70
+    kw = dict(seed=21, randomize_drone=True, randomize_platform=True, max_steps=50, auto_reset=True,
+              dtype=torch.float32, env_id_base=5000)
+    a = dd.BatchedDroneEnv(n, device=DEV, **kw); a.reset()
+    b = dd.BatchedDroneEnv(n, device=DEV, **kw); b.reset()
+    out = dd.policy_rollout(a, blob, T, sample=True, t0=3, want="arldop")
+    # (1) replay the chosen actions through the plain rollout kernel: identical environment evolution
+    rew = torch.empty(T, n, device=DEV); don = torch.empty(T, n, dtype=torch.uint8, device=DEV)
+    obs = torch.empty(T, n, 15, device=DEV)
+    b.rollout(T, "trace", actions=out["actions"], reward_out=rew, done_out=don, obs_out=obs)
+    assert torch.equal(out["reward"], rew) and torch.equal(out["done"], don)
+    for k_, v in a.get_state().items():
+        assert torch.equal(v, b.get_state()[k_]), k_
+    assert a.stats() == b.stats() and a.stats()["env_steps"] == n * T
+    # (2) obs[t] is the observation the policy saw at step t: obs[0] = reset obs, obs[t+1] = post-step obs[t]
+    c = dd.BatchedDroneEnv(n, device=DEV, **kw)
+    assert torch.equal(out["obs"][0], c.reset())
+    assert torch.equal(out["obs"][1:], obs[:-1])
+    # (3) probs are what the stand-alone forward gives on those observations (same tensor-core path)
+    for t in (0, 17, T - 1):
+        assert torch.equal(out["probs"][t], dd.policy_forward(blob, out["obs"][t].contiguous()))
+    # (4) log-prob = sum over thrusters of Bernoulli(probs).log_prob(action)  (c16:L61-63)
+    bits = torch.stack([(out["actions"] >> j) & 1 for j in range(3)], -1).float()
+    lp = torch.distributions.Bernoulli(probs=out["probs"]).log_prob(bits).sum(-1)
+    assert torch.allclose(out["logp"], lp, rtol=1e-4, atol=2e-5)
+    # (5) sampling follows the probabilities, is deterministic, and depends on t0
+    p = out["probs"].double()
+    freq, exp = bits.double().mean((0, 1)), p.mean((0, 1))
+    sd_ = (p * (1 - p)).sum((0, 1)).sqrt() / (T * n)
+    assert ((freq - exp).abs() < 6 * sd_).all(), (freq, exp)
+    a2 = dd.BatchedDroneEnv(n, device=DEV, **kw); a2.reset()
+    assert torch.equal(dd.policy_rollout(a2, blob, T, sample=True, t0=3, want="a")["actions"], out["actions"])
+    a3 = dd.BatchedDroneEnv(n, device=DEV, **kw); a3.reset()
+    assert not torch.equal(dd.policy_rollout(a3, blob, T, sample=True, t0=4, want="a")["actions"], out["actions"])
+
+
+def test_threshold_rollout_lands_with_the_trained_policy(fixture):
+    """The reference reports ~76 % landings for this checkpoint (README.md:78,108); random actions land ~3 %."""
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    n = 4096
+    e = dd.BatchedDroneEnv(n, device=DEV, seed=1, randomize_drone=True, randomize_platform=True, max_steps=500,
+                           auto_reset=True, dtype=torch.float32)
+    e.reset()
+    out = dd.policy_rollout(e, blob, 500, sample=False, want="ap")
+    s = e.stats()
+    assert s["episodes"] >= n and s["landing_rate"] > 0.3, s
+    # thresholded actions are exactly probs > 0.5
+    exp = sum(((out["probs"][..., j] > 0.5).to(torch.uint8) << j) for j in range(3))
+    assert torch.equal(out["actions"], exp)
+    print("trained policy through the fused kernel:", {k_: s[k_] for k_ in ("episodes", "landing_rate", "mean_return", "mean_length")})
+
+
+def test_policy_argument_errors(fixture):
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    e64 = dd.BatchedDroneEnv(8, device=DEV, dtype=torch.float64); e64.reset()
+    with pytest.raises(ValueError):
+        dd.policy_rollout(e64, blob, 4)
+    e = dd.BatchedDroneEnv(8, device=DEV)
+    with pytest.raises(RuntimeError):
+        dd.policy_rollout(e, blob, 4)
+    with pytest.raises(KeyError):
+        dd.PolicyBlob({"network.0.weight": torch.zeros(128, 15)}, device=DEV)
+    bad = dict(sd); bad["network.3.weight"] = torch.zeros(64, 128)
+    with pytest.raises(ValueError):
+        dd.PolicyBlob(bad, device=DEV)
+    L = nv.lib()
+    assert L.dd_policy_forward(None, None, None, 4, None) == -1
+    assert L.dd_policy_pack(None, None, None) == -1
