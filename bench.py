@@ -299,6 +299,34 @@ def run_ours(args):
     ms_roll = timed(lambda: run_rollouts(S), lambda: run_rollouts(reps))
     launches += reps
 
+    # ---- K5: fused policy rollout, BASELINE configs[3]: 65,536 envs x 250 steps, policy MLP in-kernel ----
+    k5 = None
+    if not args.no_policy:
+        fix = os.path.join(ROOT, "tests", "golden", "policy_v1.npz")
+        import numpy as np
+        d = np.load(fix)
+        sd = {kk: torch.from_numpy(d[kk]) for kk in d.files if kk.startswith("network")}
+        blob = dd.PolicyBlob(sd, device=dev)
+        NP, TP = args.policy_envs, 250
+        penv = dd.BatchedDroneEnv(NP, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                                  max_steps=MAX_STEPS, auto_reset=True, dtype=torch.float32, env_id_base=rank * NP)
+        penv.reset()
+        pbuf = dd.policy_rollout(penv, blob, TP, sample=True, want="arldo")      # allocates the rollout buffers
+        reps_p = max(2, min(10, K // 1000))
+
+        def run_policy(kk):
+            for j in range(kk):
+                dd.policy_rollout(penv, blob, TP, sample=True, t0=j * TP, want="arldo", out=pbuf)
+        ms_pol = timed(lambda: run_policy(1), lambda: run_policy(reps_p))
+        launches += reps_p
+        FLOP_STEP = 2 * (15 * 128 + 128 * 128 + 128 * 64 + 64 * 3)              # 53,376
+        steps_s = NP * TP * reps_p * ws / (ms_pol * 1e-3)
+        k5 = {"value": steps_s, "envs_per_gpu": NP, "steps_per_launch": TP, "ms_per_launch": ms_pol / reps_p,
+              "mlp_tflops": steps_s / ws * FLOP_STEP / 1e12, "flop_per_env_step": FLOP_STEP,
+              "buffers": "obs[T,N,15] f32, action u8, logp f32, reward f32, done u8 (70 B/env-step)",
+              "policy": "drone_policy_v1 (27,651 params), Bernoulli sampling, bf16 tcgen05 MMA / fp32 accumulate",
+              "stats": penv.stats(reduce=ws > 1)}
+
     # ---- e2e: HOST buffers in, HOST buffers out, every step ----
     io = [envs[s].make_host_io() for s in range(min(S, 2))]
     host_trace = traces[0][:TRACE].cpu().pin_memory()
@@ -346,6 +374,7 @@ def run_ours(args):
                               "frac": so_achieved / peak_gbs},
                 "rollout_T50_in_kernel_actions": {"value": n * T_ROLL * reps * ws / (ms_roll * 1e-3),
                                                   "ms_per_launch": ms_roll / reps, "steps_per_launch": T_ROLL},
+                "fused_policy_rollout": k5,
             },
             "e2e": {"value": n * Ke * ws / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e2e / Ke,
@@ -383,6 +412,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=300)
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-policy", action="store_true", help="skip the fused policy rollout variant (K5)")
+    ap.add_argument("--policy-envs", type=int, default=65536, help="envs per GPU for the K5 variant (BASELINE configs[3])")
     ap.add_argument("--launch-flags", type=lambda v: int(v, 0), default=0x01,
                     help="DD_LAUNCH_* bits (include/drone_b200.h): 0x01 PDL, 0x10 CTA 128, 0x20 CTA 512")
     args = ap.parse_args()

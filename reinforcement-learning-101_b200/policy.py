@@ -37,6 +37,8 @@ class PolicyBlob:
             raise ValueError("PolicyBlob lives on a CUDA device")
         params = []
         for key, shape in zip(_KEYS, _SHAPES):
+            if key not in state_dict and key[len("network."):] in state_dict:
+                key = key[len("network."):]                 # a bare nn.Sequential: '0.weight', ...
             if key not in state_dict:
                 raise KeyError(f"state_dict lacks {key!r} (expected the DroneGamerBoi layout)")
             t = state_dict[key].detach().to(device=self.device, dtype=torch.float32).contiguous()
