@@ -139,49 +139,66 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);    // .x = lo (low 16 bits)
     return *reinterpret_cast<const uint32_t*>(&p);
 }
+// max(x, 0) fused into the bf16x2 conversion (F2FP.RELU): the ReLU of the hidden layers is free
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 
-// ---- one hidden layer's epilogue: bias + LayerNorm + ReLU over N columns of my accumulator row -----
-// Pass 1 reads the row for the moments, pass 2 re-reads it and calls sink(chunk, y[32]).
-template <int N, typename Sink>
-__device__ __forceinline__ void ln_relu_epilogue(uint32_t trow, const float* __restrict__ bias,
-                                                 const float* __restrict__ gamma, const float* __restrict__ beta, Sink sink)
+// ---- one hidden layer's epilogue: bias + LayerNorm over N columns of my accumulator row -----------
+// Pass 1 reads the row for the moments, pass 2 re-reads it and calls sink(chunk, y[32]) with the
+// affine-normalised values BEFORE the ReLU (the sink applies it: for free inside the bf16 conversion
+// for layers 1-2, as FMNMX for the last hidden layer).  All element-wise arithmetic is packed fp32x2
+// (FADD2 / FFMA2, new on sm_100): two columns per instruction, which is what bounds this kernel.
+template <int N, bool BIAS, typename Sink>
+__device__ __forceinline__ void ln_epilogue(uint32_t trow, const float* __restrict__ bias,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, Sink sink)
 {
-    float sum = 0.f, sq = 0.f;
+    const float2* bias2 = reinterpret_cast<const float2*>(bias);
+    const float2* gamma2 = reinterpret_cast<const float2*>(gamma);
+    const float2* beta2 = reinterpret_cast<const float2*>(beta);
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0, q0 = s0, q1 = s0;       // 4-way ILP on the reductions
 #pragma unroll 1
     for (int c = 0; c < N / 32; ++c) {
         float v[32];
         tmem_ld32(trow + c * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float x = bias ? v[j] + bias[c * 32 + j] : v[j];
-            sum += x;
-            sq = fmaf(x, x, sq);
+        for (int j = 0; j < 16; j += 2) {
+            float2 x0 = make_float2(v[2 * j], v[2 * j + 1]), x1 = make_float2(v[2 * j + 2], v[2 * j + 3]);
+            if (BIAS) { x0 = __fadd2_rn(x0, bias2[c * 16 + j]); x1 = __fadd2_rn(x1, bias2[c * 16 + j + 1]); }
+            s0 = __fadd2_rn(s0, x0); s1 = __fadd2_rn(s1, x1);
+            q0 = __ffma2_rn(x0, x0, q0); q1 = __ffma2_rn(x1, x1, q1);
         }
     }
+    const float sum = (s0.x + s0.y) + (s1.x + s1.y), sq = (q0.x + q0.y) + (q1.x + q1.y);
     const float mean = sum * (1.0f / N);
     const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / N)), 0.f);      // biased, like nn.LayerNorm
     const float rstd = rsqrtf(var + 1e-5f);
+    const float2 r2 = make_float2(rstd, rstd), m2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll 1
     for (int c = 0; c < N / 32; ++c) {
         float v[32];
         tmem_ld32(trow + c * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float x = bias ? v[j] + bias[c * 32 + j] : v[j];
-            const float y = fmaf((x - mean) * rstd, gamma[c * 32 + j], beta[c * 32 + j]);
-            v[j] = fmaxf(y, 0.f);
+        for (int j = 0; j < 16; ++j) {
+            float2 x = make_float2(v[2 * j], v[2 * j + 1]);
+            if (BIAS) x = __fadd2_rn(x, bias2[c * 16 + j]);
+            const float2 nrm = __ffma2_rn(x, r2, m2);                      // (x - mean) * rstd
+            const float2 y = __ffma2_rn(nrm, gamma2[c * 16 + j], beta2[c * 16 + j]);
+            v[2 * j] = y.x; v[2 * j + 1] = y.y;
         }
         sink(c, v);
     }
 }
 
-// write 32 activations of my row (K columns 32c..32c+31) as bf16 into the A tile (UMMA layout)
-__device__ __forceinline__ void store_a_chunk32(uint8_t* a_tile, int row, int c, const float (&y)[32]) {
+// ReLU + write 32 activations of my row (K columns 32c..32c+31) as bf16 into the A tile (UMMA layout)
+__device__ __forceinline__ void store_a_chunk32_relu(uint8_t* a_tile, int row, int c, const float (&y)[32]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {                           // four 16-byte K chunks
         uint4 w;
-        w.x = pack_bf16(y[8 * q + 0], y[8 * q + 1]); w.y = pack_bf16(y[8 * q + 2], y[8 * q + 3]);
-        w.z = pack_bf16(y[8 * q + 4], y[8 * q + 5]); w.w = pack_bf16(y[8 * q + 6], y[8 * q + 7]);
+        w.x = pack_bf16_relu(y[8 * q + 0], y[8 * q + 1]); w.y = pack_bf16_relu(y[8 * q + 2], y[8 * q + 3]);
+        w.z = pack_bf16_relu(y[8 * q + 4], y[8 * q + 5]); w.w = pack_bf16_relu(y[8 * q + 6], y[8 * q + 7]);
         *reinterpret_cast<uint4*>(a_tile + (4 * c + q) * (kTile * 16) + row * 16) = w;
     }
 }
@@ -280,8 +297,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
-        ln_relu_epilogue<kH1>(trow, nullptr, s_par + pG0, s_par + pBe0,
-                              [&](int c, const float (&y)[32]) { store_a_chunk32(s_a, row, c, y); });
+        ln_epilogue<kH1, false>(trow, nullptr, s_par + pG0, s_par + pBe0,
+                                [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1^T ------------------------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (row == 0) {
@@ -293,8 +310,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
-        ln_relu_epilogue<kH2>(trow, s_par + pB1, s_par + pG1, s_par + pBe1,
-                              [&](int c, const float (&y)[32]) { store_a_chunk32(s_a, row, c, y); });
+        ln_epilogue<kH2, true>(trow, s_par + pB1, s_par + pG1, s_par + pBe1,
+                               [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2^T -------------------------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (row == 0) {
@@ -307,15 +324,18 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
-        float z0 = s_par[pB3 + 0], z1 = s_par[pB3 + 1], z2 = s_par[pB3 + 2];
-        ln_relu_epilogue<kH3>(trow, s_par + pB2, s_par + pG2, s_par + pBe2, [&](int c, const float (&y)[32]) {
+        float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
+        const float2* w3 = reinterpret_cast<const float2*>(s_par + pW3);
+        ln_epilogue<kH3, true>(trow, s_par + pB2, s_par + pG2, s_par + pBe2, [&](int c, const float (&y)[32]) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                z0 = fmaf(y[j], s_par[pW3 + 0 * kH3 + c * 32 + j], z0);
-                z1 = fmaf(y[j], s_par[pW3 + 1 * kH3 + c * 32 + j], z1);
-                z2 = fmaf(y[j], s_par[pW3 + 2 * kH3 + c * 32 + j], z2);
+            for (int j = 0; j < 16; ++j) {
+                const float2 h = make_float2(fmaxf(y[2 * j], 0.f), fmaxf(y[2 * j + 1], 0.f));       // ReLU
+                za = __ffma2_rn(h, w3[0 * (kH3 / 2) + c * 16 + j], za);
+                zb = __ffma2_rn(h, w3[1 * (kH3 / 2) + c * 16 + j], zb);
+                zc = __ffma2_rn(h, w3[2 * (kH3 / 2) + c * 16 + j], zc);
             }
         });
+        const float z0 = za.x + za.y + s_par[pB3 + 0], z1 = zb.x + zb.y + s_par[pB3 + 1], z2 = zc.x + zc.y + s_par[pB3 + 2];
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         const float p0 = 1.0f / (1.0f + __expf(-z0)), p1 = 1.0f / (1.0f + __expf(-z1)), p2 = 1.0f / (1.0f + __expf(-z2));
         if (pa.probs_tn && live) {
