@@ -108,6 +108,10 @@ typedef struct DDState {
     uint32_t *episode;
     uint8_t *flags;
     int32_t dtype;           /* DD_F32 / DD_F64 */
+    int32_t reserved;
+    void *prev_dist;         /* R[n] or NULL: normalised distance_to_platform of the state observed before
+                                the previous step, NaN = none (prev_state of Actor_Critic_PPO.ipynb
+                                c16:L71-72,101-102).  Needed only when a shaped-reward output is requested. */
 } DDState;
 
 /* Per-call knobs shared by reset / step / rollout. */
@@ -148,6 +152,14 @@ int dd_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, int32_
                const uint8_t *actions_tn, uint32_t t0, int32_t T,
                void *reward_tn, uint8_t *done_tn, void *obs_tn, int32_t obs_stride,
                uint64_t *stats, int64_t n, void *stream);
+
+/* dd_rollout + shaped_tn R[T][n]: the PPO notebook's client-side training reward
+ * (calc_reward, Actor_Critic_PPO.ipynb c7:L2-101, and the -500 time-out of c16:L89-93) computed in the
+ * same launch from the post-step state; needs s->prev_dist. */
+int dd_rollout_shaped(const DDState *s, const DDParams *p, const DDEnvConfig *c, int32_t policy,
+                      const uint8_t *actions_tn, uint32_t t0, int32_t T,
+                      void *reward_tn, uint8_t *done_tn, void *obs_tn, int32_t obs_stride, void *shaped_tn,
+                      uint64_t *stats, int64_t n, void *stream);
 
 /* [T][n] synthetic random action trace (same bits DD_POLICY_RANDOM uses in-kernel). */
 int dd_fill_random_actions(uint8_t *actions_tn, uint64_t seed, uint64_t env_id_base,
@@ -197,10 +209,11 @@ int dd_policy_forward(const void *blob, const float *obs, float *probs, int64_t 
 
 /* T steps of {observe, policy, act, step} in one launch; DD_F32 state only.  Optional [T][n] outputs:
  * actions (DD_ACT_* bits), logp (sum of the 3 Bernoulli log-probs), reward, done flags, obs [T][n][15],
- * probs [T][n][3]. */
+ * probs [T][n][3], shaped (the notebook's training reward; needs s->prev_dist). */
 int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, const void *blob, int32_t mode,
                       uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
-                      uint8_t *done_tn, float *obs_tn, float *probs_tn, uint64_t *stats, int64_t n, void *stream);
+                      uint8_t *done_tn, float *obs_tn, float *probs_tn, float *shaped_tn, uint64_t *stats, int64_t n,
+                      void *stream);
 
 #ifdef __cplusplus
 }

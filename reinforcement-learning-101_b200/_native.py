@@ -51,7 +51,7 @@ class DDState(C.Structure):
     _fields_ = [
         ("pos_vel", C.c_void_p), ("att_fuel", C.c_void_p), ("platform", C.c_void_p),
         ("steps", C.c_void_p), ("episode", C.c_void_p), ("flags", C.c_void_p),
-        ("dtype", C.c_int32),
+        ("dtype", C.c_int32), ("reserved", C.c_int32), ("prev_dist", C.c_void_p),
     ]
 
 
@@ -125,6 +125,8 @@ def lib():
     L.dd_step.argtypes = [PS, PP, PC, vp, vp, i32, vp, vp, vp, vp, i64, vp]
     L.dd_rollout.restype = C.c_int
     L.dd_rollout.argtypes = [PS, PP, PC, i32, vp, u32, i32, vp, vp, vp, i32, vp, i64, vp]
+    L.dd_rollout_shaped.restype = C.c_int
+    L.dd_rollout_shaped.argtypes = [PS, PP, PC, i32, vp, u32, i32, vp, vp, vp, i32, vp, vp, i64, vp]
     L.dd_fill_random_actions.restype = C.c_int
     L.dd_fill_random_actions.argtypes = [vp, u64, u64, u32, i32, i64, vp]
     L.dd_pack_actions.restype = C.c_int
@@ -142,7 +144,7 @@ def lib():
     L.dd_policy_forward.restype = C.c_int
     L.dd_policy_forward.argtypes = [vp, vp, vp, i64, vp]
     L.dd_policy_rollout.restype = C.c_int
-    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     if L.dd_abi_version() != ABI_VERSION:
         raise NativeError(f"libdrone_b200.so ABI {L.dd_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L
@@ -162,7 +164,7 @@ def default_params() -> DDParams:
 
 
 EXPORTS = (
-    "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout",
+    "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout", "dd_rollout_shaped",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
     "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout",
 )

@@ -290,6 +290,60 @@ DD_HD void speed_dist(const Env<R>& e, R& speed, R& dist)
 }
 
 // ---------------------------------------------------------------------------------------
+// N2: the PPO notebook's client-side training reward, fused as an epilogue of the step.
+// calc_reward(state, prev_state) of Actor_Critic_PPO.ipynb c7:L2-101 + the time-out rule of
+// c16:L89-93, in the notebook's statement order (restated in oracle/shaping_port.py, pinned by
+// executing the notebook's cells).  Inputs are the normalised observation fields of the
+// POST-step state (before any auto-reset); `prev_dist` is prev_state.distance_to_platform, i.e. the
+// normalised distance of the state observed before the PREVIOUS step (c16:L71-72,101-102), NaN when
+// there is none (first step of an episode).
+// ---------------------------------------------------------------------------------------
+template <typename R>
+DD_HD R shaped_reward_ppo(const Env<R>& e, uint32_t flags, R speed, R dist, R prev_dist, bool timed_out,
+                          const Consts<R>& k)
+{
+    using A = Arith<R>;
+    const R nd = A::div(dist, k.width, k.inv_width);                   // distance_to_platform
+    const R ns = A::div(speed, k.vel_norm, k.inv_vel);                 // speed
+    const R nvx = A::div(e.vx, k.vel_norm, k.inv_vel), nvy = A::div(e.vy, k.vel_norm, k.inv_vel);
+    const R ndx = A::div(e.px - e.x, k.width, k.inv_width), ndy = A::div(e.py - e.y, k.height, k.inv_height);
+    const R nang = A::div(e.angle, k.angle_norm, k.inv_angle);
+    const R nfuel = A::div(e.fuel, k.max_fuel, k.inv_fuel);
+
+    R total = (R)-0.5;                                                  // 0 + (-0.5)
+    R r_distance = (R)0, r_hover = (R)0;
+    if (prev_dist == prev_dist) {                                       // prev_state is not None
+        const R delta = prev_dist - nd;
+        const R toward = nd > (R)1e-6 ? A::add(A::mul(nvx, ndx), A::mul(nvy, ndy)) / nd : (R)0;
+        if (ns >= (R)0.15 && toward > (R)0.1 && nd > (R)0.065) {
+            R v = A::mul(A::mul(delta, (R)1000), A::add((R)1.0, A::mul(ns, (R)2.0)));
+            v = v < (R)-2 ? (R)-2 : v; v = v > (R)5 ? (R)5 : v;         // np.clip(., -2, 5)
+            r_distance = v;
+        } else if (delta < (R)-0.001) {
+            r_distance = A::mul(A::mul((R)-2.0, A::abs_(delta)), (R)1000);
+        } else if (ns < (R)0.05) {
+            r_hover = (R)-1.0;
+        } else if (ns < (R)0.15) {
+            r_hover = (R)-0.3;
+        }
+    }
+    total = A::add(total, r_distance);
+    total = A::add(total, r_hover);
+    const R excess = A::abs_(nang) - A::add(A::mul((R)(0.20 - 0.111), nd), (R)0.111);
+    total = A::add(total, excess > (R)0 ? -excess : (R)0);
+    const R over = nd < (R)1 ? A::mul((R)-2, (ns - (R)0.1 > (R)0 ? ns - (R)0.1 : (R)0))
+                             : A::mul((R)-1, (ns - (R)0.6 > (R)0 ? ns - (R)0.6 : (R)0));
+    total = A::add(total, over);
+    total = A::add(total, ndy > (R)0 ? (R)0 : A::mul(ndy, (R)4.0));
+    R terminal = (R)0;
+    if (flags & DD_LANDED) terminal = A::add((R)800.0, A::mul(nfuel, (R)100.0));
+    else if (flags & DD_CRASHED) terminal = nd > (R)0.3 ? (R)-300.0 : (R)-200.0;
+    total = A::add(total, terminal);
+    if (timed_out && !(flags & DD_LANDED)) total -= (R)500;             // c16:L89-93
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: the spawn of episode k of
 // global env g under seed s is a pure function of (s, g, k), whatever the grid or GPU count.
 // ---------------------------------------------------------------------------------------

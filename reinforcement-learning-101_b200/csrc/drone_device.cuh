@@ -12,7 +12,7 @@ constexpr int kMaxObsStride = 16;
 
 template <typename R>
 struct KArgs {
-    R *pos_vel, *att_fuel, *platform;
+    R *pos_vel, *att_fuel, *platform, *prev_dist;
     int32_t* steps;
     uint32_t* episode;
     uint8_t* flags;
@@ -107,6 +107,10 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+template <typename R> __device__ __forceinline__ R nan_of();
+template <> __device__ __forceinline__ float nan_of<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double nan_of<double>() { return __longlong_as_double(0x7ff8000000000000ll); }
+
 __device__ __forceinline__ long long return_fx(double ret) { return __double2ll_rn(ret * DD_RETURN_FIXED_SCALE); }
 
 // Called by ALL 32 lanes of a warp (f == 0 in lanes whose episode goes on).  Costs one ballot in

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ KAr
                     spawn(e, k, a.seed, a.env_id_base + (uint64_t)i, ep, a.rand_drone != 0, a.rand_platform != 0);
                     a.episode[i] = ep + 1;
                     store2(a.platform, i, e.px, e.py);
+                    if (a.prev_dist) a.prev_dist[i] = nan_of<R>();
                     f = 0;
                     if (OBS) speed_dist(e, speed, dist);
                 }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ K
     store_env(a, i, e);
     store2(a.platform, i, e.px, e.py);
     a.flags[i] = 0;
+    if (a.prev_dist) a.prev_dist[i] = nan_of<R>();              // prev_state = None (c16:L38)
     if (a.obs) {
         R speed, dist;
         speed_dist(e, speed, dist);
@@ -159,6 +161,7 @@ struct RArgs {
     R* reward_tn;
     uint8_t* done_tn;
     R* obs_tn;
+    R* shaped_tn;
     uint32_t t0;
     int32_t T, policy, auto_reset;
 };
@@ -188,11 +191,20 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     const uint64_t gid = a.env_id_base + (uint64_t)i;
     U4 blk = {0, 0, 0, 0};
     uint32_t blk_id = 0xffffffffu;
+    // N2 (shaped training reward): normalised distance of the current state and of the one before it
+    const bool shaping = ra.shaped_tn != nullptr;
+    R dprev = nan_of<R>(), dcur = (R)0;
+    if (live && shaping) {
+        R s_, d_;
+        speed_dist(e, s_, d_);
+        dcur = Arith<R>::div(d_, k.width, k.inv_width);
+        dprev = a.prev_dist[i];
+    }
 
     for (int32_t t = 0; t < ra.T; ++t) {
         uint32_t oflags = pflags, f_stat = 0;
         double ret_stat = 0.0; int32_t len_stat = 0;
-        R reward = (R)0, speed = (R)0, dist = (R)0;
+        R reward = (R)0, speed = (R)0, dist = (R)0, shaped = (R)0;
         if (live) {
             const size_t o = (size_t)t * a.n + i;
             uint32_t act;
@@ -209,6 +221,12 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                 uint32_t f = step_core<R, OBS>(e, act, k, reward, speed, dist);
                 if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
                 oflags = f;
+                if (shaping) {
+                    const R sp = OBS ? speed : Arith<R>::sqrt_(Arith<R>::fma_(e.vx, e.vx, Arith<R>::mul(e.vy, e.vy)));
+                    shaped = shaped_reward_ppo(e, f, sp, dist, dprev, a.max_steps > 0 && e.steps >= a.max_steps, k);
+                    dprev = dcur;
+                    dcur = Arith<R>::div(dist, k.width, k.inv_width);
+                }
                 if (f) {
                     f_stat = f; ret_stat = (double)e.ret; len_stat = e.steps;
                     if (ra.auto_reset) {
@@ -216,13 +234,15 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                         ep += 1;
                         platform_dirty = true;
                         f = 0;
-                        if (OBS) speed_dist(e, speed, dist);
+                        if (OBS || shaping) speed_dist(e, speed, dist);
+                        if (shaping) { dprev = nan_of<R>(); dcur = Arith<R>::div(dist, k.width, k.inv_width); }
                     }
                 }
                 pflags = f;
             } else if (OBS) {
                 speed_dist(e, speed, dist);
             }
+            if (shaping) ra.shaped_tn[o] = shaped;
             if (ra.reward_tn) ra.reward_tn[o] = reward;
             if (ra.done_tn) ra.done_tn[o] = (uint8_t)oflags;
             if (OBS) {
@@ -243,6 +263,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
         a.flags[i] = (uint8_t)pflags;
         a.episode[i] = ep;
         if (platform_dirty) store2(a.platform, i, e.px, e.py);
+        if (shaping) a.prev_dist[i] = dprev;
     }
 }
 
@@ -315,6 +336,7 @@ static int fill_args(KArgs<R>& a, const DDState* s, const DDParams* p, const DDE
     if (reinterpret_cast<uintptr_t>(s->platform) & (2 * sizeof(R) - 1)) return DD_E_ALIGN;
     a = KArgs<R>{};
     a.pos_vel = (R*)s->pos_vel; a.att_fuel = (R*)s->att_fuel; a.platform = (R*)s->platform;
+    a.prev_dist = (R*)s->prev_dist;
     a.steps = s->steps; a.episode = s->episode; a.flags = s->flags;
     a.n = (uint32_t)n; a.seed = c->seed; a.env_id_base = c->env_id_base;
     a.max_steps = c->max_steps; a.obs_stride = DD_OBS_DIM;
@@ -394,7 +416,7 @@ static int step_impl(const DDState* s, const DDParams* p, const DDEnvConfig* c, 
 template <typename R>
 static int rollout_impl(const DDState* s, const DDParams* p, const DDEnvConfig* c, int32_t policy,
                         const uint8_t* actions_tn, uint32_t t0, int32_t T, void* reward_tn, uint8_t* done_tn,
-                        void* obs_tn, int32_t obs_stride, uint64_t* stats, int64_t n, cudaStream_t st)
+                        void* obs_tn, int32_t obs_stride, void* shaped_tn, uint64_t* stats, int64_t n, cudaStream_t st)
 {
     RArgs<R> ra{};
     if (int rc = fill_args(ra.a, s, p, c, n)) return rc;
@@ -403,7 +425,9 @@ static int rollout_impl(const DDState* s, const DDParams* p, const DDEnvConfig* 
     if (T < 0) return DD_E_RANGE;
     if (obs_tn) { if (int rc = check_stride(obs_stride)) return rc; ra.a.obs_stride = obs_stride; }
     ra.a.stats = (unsigned long long*)stats;
+    if (shaped_tn && !s->prev_dist && n > 0) return DD_E_NULL;
     ra.actions_tn = actions_tn; ra.reward_tn = (R*)reward_tn; ra.done_tn = done_tn; ra.obs_tn = (R*)obs_tn;
+    ra.shaped_tn = (R*)shaped_tn;
     ra.t0 = t0; ra.T = T; ra.policy = policy; ra.auto_reset = c->auto_reset;
     if (n == 0 || T == 0) return 0;
     const bool pdl = (c->launch_flags & DD_LAUNCH_PDL) != 0, def = params_are_default(*p);
@@ -461,16 +485,23 @@ int dd_step(const DDState* s, const DDParams* p, const DDEnvConfig* c, const uin
     return DD_E_DTYPE;
 }
 
+int dd_rollout_shaped(const DDState* s, const DDParams* p, const DDEnvConfig* c, int32_t policy,
+                      const uint8_t* actions_tn, uint32_t t0, int32_t T, void* reward_tn, uint8_t* done_tn,
+                      void* obs_tn, int32_t obs_stride, void* shaped_tn, uint64_t* stats, int64_t n, void* stream)
+{
+    if (!s) return DD_E_NULL;
+    if (s->dtype == DD_F32)
+        return dd::rollout_impl<float>(s, p, c, policy, actions_tn, t0, T, reward_tn, done_tn, obs_tn, obs_stride, shaped_tn, stats, n, (cudaStream_t)stream);
+    if (s->dtype == DD_F64)
+        return dd::rollout_impl<double>(s, p, c, policy, actions_tn, t0, T, reward_tn, done_tn, obs_tn, obs_stride, shaped_tn, stats, n, (cudaStream_t)stream);
+    return DD_E_DTYPE;
+}
+
 int dd_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, int32_t policy,
                const uint8_t* actions_tn, uint32_t t0, int32_t T, void* reward_tn, uint8_t* done_tn,
                void* obs_tn, int32_t obs_stride, uint64_t* stats, int64_t n, void* stream)
 {
-    if (!s) return DD_E_NULL;
-    if (s->dtype == DD_F32)
-        return dd::rollout_impl<float>(s, p, c, policy, actions_tn, t0, T, reward_tn, done_tn, obs_tn, obs_stride, stats, n, (cudaStream_t)stream);
-    if (s->dtype == DD_F64)
-        return dd::rollout_impl<double>(s, p, c, policy, actions_tn, t0, T, reward_tn, done_tn, obs_tn, obs_stride, stats, n, (cudaStream_t)stream);
-    return DD_E_DTYPE;
+    return dd_rollout_shaped(s, p, c, policy, actions_tn, t0, T, reward_tn, done_tn, obs_tn, obs_stride, nullptr, stats, n, stream);
 }
 
 int dd_fill_random_actions(uint8_t* actions_tn, uint64_t seed, uint64_t env_id_base, uint32_t t0, int32_t T,

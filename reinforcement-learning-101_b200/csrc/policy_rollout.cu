@@ -70,6 +70,7 @@ struct PArgs {
     uint8_t* done_tn;
     float* obs_tn;             // [T][n][15]
     float* probs_tn;           // [T][n][3] (optional)
+    float* shaped_tn;          // [T][n] notebook training reward (optional)
     const float* obs_in;       // forward-only mode: [n][15], no env stepping
     int32_t auto_reset;
 };
@@ -265,6 +266,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint64_t gid = a.env_id_base + (uint64_t)i;
     float speed = 0.f, dist = 0.f;
     if (!forward_only) speed_dist(e, speed, dist);
+    const bool shaping = pa.shaped_tn != nullptr;
+    float dprev = nan_of<float>(), dcur = dist * k.inv_width;
+    if (live && shaping) dprev = a.prev_dist[i];
 
     for (int32_t t = 0; t < pa.T; ++t) {
         const size_t o = (size_t)t * a.n + i;
@@ -366,12 +370,17 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         // ---------------- environment step (same code as K1) -------------------------------------------
         uint32_t oflags = pflags, f_stat = 0;
         double ret_stat = 0.0; int32_t len_stat = 0;
-        float reward = 0.f;
+        float reward = 0.f, shaped = 0.f;
         if (live) {
             if (!(pflags & DD_DONE)) {
                 uint32_t f = step_core<float, true>(e, act, k, reward, speed, dist);
                 if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
                 oflags = f;
+                if (shaping) {
+                    shaped = shaped_reward_ppo(e, f, speed, dist, dprev, a.max_steps > 0 && e.steps >= a.max_steps, k);
+                    dprev = dcur;
+                    dcur = Arith<float>::div(dist, k.width, k.inv_width);
+                }
                 if (f) {
                     f_stat = f; ret_stat = (double)e.ret; len_stat = e.steps;
                     if (pa.auto_reset) {
@@ -380,10 +389,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                         platform_dirty = true;
                         f = 0;
                         speed_dist(e, speed, dist);
+                        if (shaping) { dprev = nan_of<float>(); dcur = Arith<float>::div(dist, k.width, k.inv_width); }
                     }
                 }
                 pflags = f;
             }
+            if (shaping) pa.shaped_tn[o] = shaped;
             if (pa.actions_tn) pa.actions_tn[o] = (uint8_t)act;
             if (pa.logp_tn) pa.logp_tn[o] = logp;
             if (pa.reward_tn) pa.reward_tn[o] = reward;
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         a.flags[i] = (uint8_t)pflags;
         a.episode[i] = ep;
         if (platform_dirty) store2(a.platform, i, e.px, e.py);
+        if (shaping) a.prev_dist[i] = dprev;
     }
     // ---- teardown: everyone is done with TMEM, then the allocating warp frees it ----
     tc_fence_before();
@@ -479,7 +491,7 @@ int dd_policy_forward(const void* blob, const float* obs, float* probs, int64_t 
 
 int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob, int32_t mode,
                       uint32_t t0, int32_t T, uint8_t* actions_tn, float* logp_tn, float* reward_tn, uint8_t* done_tn,
-                      float* obs_tn, float* probs_tn, uint64_t* stats, int64_t n, void* stream)
+                      float* obs_tn, float* probs_tn, float* shaped_tn, uint64_t* stats, int64_t n, void* stream)
 {
     if (!s || !p || !c || !blob) return DD_E_NULL;
     if (s->dtype != DD_F32) return DD_E_DTYPE;                 // the fused kernel is the fp32 throughput path
@@ -488,8 +500,10 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     if (n > 0 && (!s->pos_vel || !s->att_fuel || !s->platform || !s->steps || !s->episode || !s->flags)) return DD_E_NULL;
     if ((reinterpret_cast<uintptr_t>(s->pos_vel) | reinterpret_cast<uintptr_t>(s->att_fuel) | reinterpret_cast<uintptr_t>(blob)) & 15u) return DD_E_ALIGN;
     if (reinterpret_cast<uintptr_t>(s->platform) & 7u) return DD_E_ALIGN;
+    if (shaped_tn && !s->prev_dist && n > 0) return DD_E_NULL;
     if (n == 0 || T == 0) return 0;
     dd::PArgs pa{};
+    pa.a.prev_dist = (float*)s->prev_dist; pa.shaped_tn = shaped_tn;
     pa.a.pos_vel = (float*)s->pos_vel; pa.a.att_fuel = (float*)s->att_fuel; pa.a.platform = (float*)s->platform;
     pa.a.steps = s->steps; pa.a.episode = s->episode; pa.a.flags = s->flags;
     pa.a.stats = (unsigned long long*)stats;

