@@ -327,6 +327,26 @@ def run_ours(args):
               "policy": "drone_policy_v1 (27,651 params), Bernoulli sampling, bf16 tcgen05 MMA / fp32 accumulate",
               "stats": penv.stats(reduce=ws > 1)}
 
+    # ---- BASELINE configs[4]: curriculum sweep 75 -> 250, 2M envs per GPU, stats all-reduced over ranks ----
+    cur = None
+    if not args.no_curriculum:
+        NC = args.curriculum_envs
+        cenv = dd.BatchedDroneEnv(NC, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                                  auto_reset=False, dtype=torch.float32, env_id_base=rank * NC)
+        caps = dd.step_schedule(8, 75, 250).tolist()
+        dd.collect_episodes(cenv, caps[0], policy="bangbang", reduce=ws > 1)           # warm-up
+        stages = []
+
+        def run_sweep():
+            stages[:] = dd.curriculum_sweep(cenv, caps, policy="bangbang", reduce=ws > 1)
+        ms_cur = timed(lambda: None, run_sweep)
+        launches += 2 * len(caps)
+        cur = {"envs_total": NC * ws, "caps": caps, "ms_total": ms_cur,
+               "env_steps_per_s": sum(s_["env_steps"] for s_ in stages) / (ms_cur * 1e-3),
+               "policy": "bang-bang (main = vy > 1.5), one episode per env per stage, freeze after done",
+               "stages": [{k_: s_[k_] for k_ in ("max_steps", "success_rate", "avg_reward", "avg_steps")} for s_ in stages]}
+        del cenv
+
     # ---- e2e: HOST buffers in, HOST buffers out, every step ----
     io = [envs[s].make_host_io() for s in range(min(S, 2))]
     host_trace = traces[0][:TRACE].cpu().pin_memory()
@@ -375,6 +395,7 @@ def run_ours(args):
                 "rollout_T50_in_kernel_actions": {"value": n * T_ROLL * reps * ws / (ms_roll * 1e-3),
                                                   "ms_per_launch": ms_roll / reps, "steps_per_launch": T_ROLL},
                 "fused_policy_rollout": k5,
+                "curriculum_sweep": cur,
             },
             "e2e": {"value": n * Ke * ws / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e2e / Ke,
@@ -413,6 +434,8 @@ def main():
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy", action="store_true", help="skip the fused policy rollout variant (K5)")
+    ap.add_argument("--no-curriculum", action="store_true", help="skip the curriculum sweep variant (cfg 5)")
+    ap.add_argument("--curriculum-envs", type=int, default=1 << 21, help="envs per GPU in the curriculum sweep")
     ap.add_argument("--policy-envs", type=int, default=65536, help="envs per GPU for the K5 variant (BASELINE configs[3])")
     ap.add_argument("--launch-flags", type=lambda v: int(v, 0), default=0x01,
                     help="DD_LAUNCH_* bits (include/drone_b200.h): 0x01 PDL, 0x10 CTA 128, 0x20 CTA 512")

@@ -16,7 +16,8 @@ from .distributed import (allreduce_moments, allreduce_stats, init_from_env, mea
 
 __all__ = ["native", "build_native", "BatchedDroneEnv", "StepInfo", "gae", "advantage_moments",
            "normalize_advantages", "allreduce_stats", "allreduce_moments", "shard_range", "stats_dict",
-           "mean_std_from_moments", "init_from_env", "PolicyBlob", "policy_forward", "policy_rollout"]
+           "mean_std_from_moments", "init_from_env", "PolicyBlob", "policy_forward", "policy_rollout",
+           "step_schedule", "collect_episodes", "curriculum_sweep"]
 
 
 def __getattr__(name):
@@ -31,7 +32,10 @@ def __getattr__(name):
     if name in ("PolicyBlob", "policy_forward", "policy_rollout"):
         from . import policy
         return getattr(policy, name)
-    if name in ("compat", "env", "ppo_ops", "policy"):
+    if name in ("step_schedule", "collect_episodes", "curriculum_sweep"):
+        from . import curriculum
+        return getattr(curriculum, name)
+    if name in ("compat", "env", "ppo_ops", "policy", "curriculum"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

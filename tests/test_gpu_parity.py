@@ -462,3 +462,27 @@ def test_full_size_properties():
     sc = c.stats()
     # fp32 threshold flips may move a handful of episodes between classes
     assert abs(sc["episodes"] - ost.episodes) <= 8 and abs(sc["landed"] - ost.landed) <= 4
+
+
+# =================================================================================================
+# BASELINE configs[4]: curriculum sweep -- one episode per env per stage, device-reduced statistics
+# =================================================================================================
+def test_curriculum_sweep_matches_oracle():
+    n = 3000
+    caps = dd.step_schedule(4, 75, 250).tolist()
+    env = dd.BatchedDroneEnv(n, device="cuda:0", seed=13, randomize_drone=True, randomize_platform=True,
+                             auto_reset=False, dtype=torch.float64)
+    stages = dd.curriculum_sweep(env, caps, policy="bangbang", reduce=False)
+    o = co.OracleBatch(n, seed=13, randomize_drone=True, randomize_platform=True, auto_reset=False)
+    for cap, st in zip(caps, stages):
+        o.max_steps = cap
+        o.reset()
+        _, _, os_ = o.rollout(cap, policy=co.POL_BANGBANG)
+        assert st["max_steps"] == cap and st["num_games"] == n == os_.episodes       # exactly one episode per env
+        assert (st["num_successes"], st["crashed"], st["timed_out"]) == (os_.landed, os_.crashed, os_.truncated)
+        assert st["avg_steps"] == os_.sum_length / n
+        assert st["avg_reward"] == pytest.approx(os_.sum_return / n, rel=1e-9, abs=1e-5)
+    rates = [s["success_rate"] for s in stages]
+    assert rates == sorted(rates) and rates[-1] > rates[0]      # longer caps let more bang-bang episodes land
+    with pytest.raises(ValueError):
+        dd.collect_episodes(dd.BatchedDroneEnv(8, device="cuda:0", auto_reset=True), 10)

@@ -149,3 +149,13 @@ def test_gloo_world_size_2(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0]
     assert line == "RESULT 1001 3 -3.0 20020 [1001.0, 501.0, 5.0]", line
+
+
+def test_step_schedule_is_the_notebook_formula():
+    """Actor_Critic_PPO.ipynb c19:L13-17 (300 -> 500) and README.md:55 (75 -> 250)."""
+    import numpy as np
+    s = dd.step_schedule(2000)
+    x = np.linspace(0, 1, num=2000)
+    assert np.array_equal(s, np.round(300 + 200 * x ** 0.65).astype(np.int32))
+    assert s[0] == 300 and s[-1] == 500 and s.dtype == np.int32 and np.all(np.diff(s) >= 0)
+    assert dd.step_schedule(8, 75, 250).tolist() == [75, 124, 153, 176, 197, 216, 233, 250]
