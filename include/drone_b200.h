@@ -3,7 +3,8 @@
  *
  * Plain C, plain pointers and sizes, no torch types.  Every entry point is a pure
  * function over caller-owned DEVICE buffers: no global state, no allocation, no
- * host synchronisation; work is enqueued on the cudaStream_t passed in (as void*).
+ * host synchronisation (one documented exception: dd_policy_pack); work is enqueued
+ * on the cudaStream_t passed in (as void*).
  * Return value: 0 = ok, < 0 = argument error (DD_E_*), > 0 = cudaError_t.
  * Safe to call concurrently on different streams / devices.
  *
@@ -20,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DD_ABI_VERSION 1
+#define DD_ABI_VERSION 2
 
 /* ---- flag byte (per-step output and persistent state) ---------------------- */
 #define DD_DONE        0x01u   /* game_engine.py:53  self.done            */
@@ -197,21 +198,36 @@ typedef struct DDPolicy {
     const float *w3, *b3;                 /* network.9 (Linear 64->3) */
 } DDPolicy;
 
-#define DD_POLICY_BLOB_BYTES 57360        /* device workspace filled by dd_policy_pack */
+#define DD_POLICY_BLOB_BYTES 62736        /* device workspace filled by dd_policy_pack */
 #define DD_ACTION_THRESHOLD 0             /* action = probs > 0.5        (c18:L24-25) */
 #define DD_ACTION_SAMPLE    1             /* action ~ Bernoulli(probs)   (c16:L61-63), Philox */
 
-/* fp32 torch parameters -> bf16 tensor-core operand images + fp32 LN parameters (16-byte aligned blob). */
-int dd_policy_pack(const DDPolicy *p, void *blob, void *stream);
+/* The per-column fp32 parameters the CUDA cores apply after each tensor-core layer.  HOST memory: the
+ * launch passes them by value (kernel-argument constant bank), so every thread reads them as uniform
+ * operands instead of replicating shared-memory loads.  Filled by dd_policy_pack. */
+typedef struct DDPolicyConsts {
+    float inv_gamma0[128], beta0[128];    /* network.1: 1 / LayerNorm.weight (|w| floored at 1e-12), LayerNorm.bias */
+    float inv_gamma1[128], beta1[128];    /* network.4 */
+    float inv_gamma2[64],  beta2[64];     /* network.7 */
+    float w3[3][64];                      /* network.9.weight */
+    float b3[4];                          /* network.9.bias (+ pad) */
+} DDPolicyConsts;
+
+/* fp32 torch parameters (DEVICE pointers) -> `blob` (device, 16-byte aligned): bf16 tensor-core operand
+ * images with the LayerNorm centring, gamma and the biases folded in; and `consts` (HOST).  This is the one
+ * entry point that synchronises `stream` (it copies 3.3 KB back to fill `consts`); call it once per policy
+ * update. */
+int dd_policy_pack(const DDPolicy *p, void *blob, DDPolicyConsts *consts, void *stream);
 
 /* probs[n][3] = policy(obs[n][15]) through the same tcgen05 path the rollout uses (parity hook). */
-int dd_policy_forward(const void *blob, const float *obs, float *probs, int64_t n, void *stream);
+int dd_policy_forward(const void *blob, const DDPolicyConsts *consts, const float *obs, float *probs, int64_t n,
+                      void *stream);
 
 /* T steps of {observe, policy, act, step} in one launch; DD_F32 state only.  Optional [T][n] outputs:
  * actions (DD_ACT_* bits), logp (sum of the 3 Bernoulli log-probs), reward, done flags, obs [T][n][15],
  * probs [T][n][3], shaped (the notebook's training reward; needs s->prev_dist). */
-int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, const void *blob, int32_t mode,
-                      uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
+int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, const void *blob,
+                      const DDPolicyConsts *consts, int32_t mode, uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
                       uint8_t *done_tn, float *obs_tn, float *probs_tn, float *shaped_tn, uint64_t *stats, int64_t n,
                       void *stream);
 

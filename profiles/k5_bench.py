@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Stand-alone timing of K5 (the fused policy rollout, BASELINE configs[3]: 65,536 envs x 250 steps) --
+the same call bench.py's `fused_policy_rollout` variant makes, without the rest of the bench, so that an
+`ncu --set full -k regex:policy_rollout -c 1` capture of it takes seconds.
+    python profiles/k5_bench.py [--envs 65536] [--T 250] [--reps 10] [--want arldo] [--threshold]
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+dd = importlib.import_module("reinforcement-learning-101_b200")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--T", type=int, default=250)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--want", default="arldo")
+    ap.add_argument("--threshold", action="store_true")
+    args = ap.parse_args()
+    dev = "cuda:0"
+    d = np.load(os.path.join(ROOT, "tests", "golden", "policy_v1.npz"))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files if k.startswith("network")}
+    blob = dd.PolicyBlob(sd, device=dev)
+    env = dd.BatchedDroneEnv(args.envs, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                             max_steps=250, auto_reset=True, dtype=torch.float32)
+    env.reset()
+    buf = dd.policy_rollout(env, blob, args.T, sample=not args.threshold, want=args.want)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for j in range(args.reps):
+        dd.policy_rollout(env, blob, args.T, sample=not args.threshold, t0=(j + 1) * args.T, want=args.want, out=buf)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.reps
+    steps = args.envs * args.T
+    print(json.dumps({"kernel": "policy_rollout_kernel", "envs": args.envs, "T": args.T, "want": args.want,
+                      "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
+                      "mlp_tflops": steps * 53376 / ms * 1e3 / 1e12, "stats": env.stats()}))
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ NVCC_FLAGS = (
 )
 
 # ---- constants of include/drone_b200.h ------------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 DONE, LANDED, CRASHED, TRUNCATED = 0x01, 0x02, 0x04, 0x08
 CAUSE_MASK, CAUSE_GROUND, CAUSE_FUEL, CAUSE_OOB = 0x30, 0x10, 0x20, 0x30
 ACT_MAIN, ACT_LEFT, ACT_RIGHT, ACT_SKIP = 0x01, 0x02, 0x04, 0x80
@@ -68,6 +68,14 @@ class DDPolicy(C.Structure):
     """Device pointers to the fp32 parameters of the 15-128-128-64-3 LayerNorm MLP."""
     _fields_ = [(k, C.c_void_p) for k in (
         "w0", "b0", "g0", "be0", "w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "w3", "b3")]
+
+
+class DDPolicyConsts(C.Structure):
+    """Host-side per-column parameters of the fused policy kernel (passed by value at launch)."""
+    _fields_ = [("inv_gamma0", C.c_float * 128), ("beta0", C.c_float * 128),
+                ("inv_gamma1", C.c_float * 128), ("beta1", C.c_float * 128),
+                ("inv_gamma2", C.c_float * 64), ("beta2", C.c_float * 64),
+                ("w3", (C.c_float * 64) * 3), ("b3", C.c_float * 4)]
 
 
 def nvcc_path() -> str:
@@ -140,11 +148,11 @@ def lib():
     L.dd_gae.restype = C.c_int
     L.dd_gae.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp]
     L.dd_policy_pack.restype = C.c_int
-    L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, vp]
+    L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
     L.dd_policy_forward.restype = C.c_int
-    L.dd_policy_forward.argtypes = [vp, vp, vp, i64, vp]
+    L.dd_policy_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
     L.dd_policy_rollout.restype = C.c_int
-    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, C.POINTER(DDPolicyConsts), i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     if L.dd_abi_version() != ABI_VERSION:
         raise NativeError(f"libdrone_b200.so ABI {L.dd_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L

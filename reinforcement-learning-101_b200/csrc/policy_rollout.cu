@@ -14,17 +14,25 @@
 //     memory (UMMA K-major, no-swizzle canonical layout), fp32 accumulators in TMEM (128 columns
 //     per tile, 512 = the whole TMEM per CTA), issued by one elected thread per tile and tracked with
 //     `tcgen05.commit` -> mbarrier;
-//   * LayerNorm + ReLU + the bf16 re-quantisation of the next layer's A operand are the epilogue:
-//     each thread reads its accumulator row with `tcgen05.ld.32x32b.x32` (SASS LDTM), twice (moments,
-//     then normalise), and writes the next A tile straight into the UMMA layout;
+//   * LayerNorm is folded into the GEMM operands by dd_policy_pack.  With C = I - 11^T/N (centring
+//     over the N outputs) and G = diag(gamma): the weight image is bf16(G C W), the bias G C b rides in
+//     an extra K = 16 block (a constant "ones" A block x a [N][16] image holding the bias split into
+//     bf16 hi + lo), so the accumulator row is  x''_j = gamma_j (x_j - mean(x)).  What is left for the
+//     CUDA cores is  var = 1/N sum_j (x''_j / gamma_j)^2  (pass 1: FMUL2 + FFMA2 per column pair) and
+//     y_j = x''_j * rstd + beta_j  (pass 2: one FFMA2, ReLU inside the bf16 conversion), i.e. 4
+//     instructions per pair instead of 7 and a third of the shared-memory parameter traffic;
+//   * each thread reads its accumulator row with `tcgen05.ld.32x32b.x32` (SASS LDTM), twice,
+//     double-buffered (chunk c+1 is in flight while chunk c is processed) and writes the next A tile
+//     straight into the UMMA layout;
 //   * weights (bf16, already in UMMA layout) + LN parameters live in shared memory for the whole
-//     kernel (57 KB), the A tiles take 32 KB per tile: 185 KB of the 227 KB;
+//     kernel (61 KB) + the ones block (4 KB), the A tiles take 32 KB per tile: 194 KB of the 227 KB;
 //   * the last layer (64 -> 3) and the sigmoid / Bernoulli / log-prob are folded into the third
 //     epilogue on the CUDA cores; the environment step is `step_core` from drone_core.cuh, the
 //     same code as K1, so the environment side is bit-identical to dd_rollout on the same actions.
 // The four tiles of a CTA are independent pipelines, so while one waits for its MMAs the other three
-// keep the CUDA cores busy: this kernel is bound by the epilogue arithmetic (~2.5 k instructions per
-// env-step), not by the tensor pipe.
+// keep the CUDA cores busy; work that does not depend on the network output (Philox draws, the
+// observation stores) is placed under the first MMA.  The kernel is bound by the epilogue arithmetic
+// and its latencies (4 warps per scheduler), not by the tensor pipe (profiles/README.md).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -39,26 +47,33 @@ constexpr int kPolThreads = kTile * kGroups;   // 512
 constexpr int kH1 = 128, kH2 = 128, kH3 = 64, kIn = 15, kInPad = 16, kOut = 3;
 
 // ---- parameter blob (device memory, produced by policy_pack_kernel; copied verbatim to smem) ----
-// bf16 weight images in UMMA K-major no-swizzle layout: element (n, k) of a [N][K] matrix sits at
+// bf16 operand images in UMMA K-major no-swizzle layout: element (n, k) of a [N][K] matrix sits at
 // byte (k / 8) * (N * 16) + n * 16 + (k % 8) * 2   (8x16-byte core matrices; LBO = N*16, SBO = 128)
-constexpr int kW0Off = 0;                                  // [128][16]  (col 15 = bias b0: obs[15] := 1)
-constexpr int kW1Off = kW0Off + kH1 * kInPad * 2;          // [128][128]
-constexpr int kW2Off = kW1Off + kH2 * kH1 * 2;             // [64][128]
-constexpr int kParOff = kW2Off + kH3 * kH2 * 2;            // fp32 parameters
-// fp32 parameter order
-constexpr int pG0 = 0, pBe0 = 128, pB1 = 256, pG1 = 384, pBe1 = 512, pB2 = 640, pG2 = 704, pBe2 = 768,
-              pW3 = 832, pB3 = 1024, kParFloats = 1028;
-constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 57,360
+constexpr int kW0Off = 0;                                  // [128][16]  G0 C0 [W0 | b0]  (obs[15] := 1)
+constexpr int kW1Off = kW0Off + kH1 * kInPad * 2;          // [128][128] G1 C1 W1
+constexpr int kW1bOff = kW1Off + kH2 * kH1 * 2;            // [128][16]  col 0/1 = hi/lo of G1 C1 b1
+constexpr int kW2Off = kW1bOff + kH2 * 16 * 2;             // [64][128]  G2 C2 W2
+constexpr int kW2bOff = kW2Off + kH3 * kH2 * 2;            // [64][16]   col 0/1 = hi/lo of G2 C2 b2
+constexpr int kParOff = kW2bOff + kH3 * 16 * 2;            // fp32 parameters
+// fp32 parameter order: 1/gamma and beta per LayerNorm, then the last Linear
+constexpr int pIg0 = 0, pBe0 = 128, pIg1 = 256, pBe1 = 384, pIg2 = 512, pBe2 = 576, pW3 = 640, pB3 = 832,
+              kParFloats = 836;
+constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 62,736
 static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
 static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
+static_assert(sizeof(DDPolicyConsts) == kParFloats * 4, "the blob's fp32 section is a DDPolicyConsts image");
+constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this is treated as +-1e-12
 
 constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
 constexpr int kSmemBlob = 0;
-constexpr int kSmemA = ((kBlobBytes + 1023) / 1024) * 1024;
+constexpr int kSmemOnes = ((kParOff + 1023) / 1024) * 1024;      // [128][16] bf16: columns 0, 1 = 1.0
+constexpr int kOnesBytes = kTile * 16 * 2;
+constexpr int kSmemA = kSmemOnes + kOnesBytes;
 constexpr int kSmemBar = kSmemA + kGroups * kABytes;
 constexpr int kSmemTotal = kSmemBar + 64;
 
 struct PArgs {
+    DDPolicyConsts pc;     // per-column LN parameters + last layer: constant bank -> uniform operands
     KArgs<float> a;        // env state pointers etc.
     const uint8_t* blob;
     int32_t mode;              // DD_SAMPLE_*
@@ -121,9 +136,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 consecutive fp32 columns of this thread's TMEM lane.  Issue and wait are split so the next chunk
+// can be in flight while this one is processed.  `tcgen05.wait::ld` covers every load the thread has
+// issued; the registers are threaded through the wait statements as in/out operands so the compiler
+// cannot schedule a consumer above the wait.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -132,9 +149,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+    asm volatile(""
+                 : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ float2 f2_of(const uint32_t (&r)[32], int pair) {
+    return make_float2(__uint_as_float(r[2 * pair]), __uint_as_float(r[2 * pair + 1]));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);    // .x = lo (low 16 bits)
@@ -147,49 +174,51 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
     return d;
 }
 
-// ---- one hidden layer's epilogue: bias + LayerNorm over N columns of my accumulator row -----------
-// Pass 1 reads the row for the moments, pass 2 re-reads it and calls sink(chunk, y[32]) with the
-// affine-normalised values BEFORE the ReLU (the sink applies it: for free inside the bf16 conversion
-// for layers 1-2, as FMNMX for the last hidden layer).  All element-wise arithmetic is packed fp32x2
-// (FADD2 / FFMA2, new on sm_100): two columns per instruction, which is what bounds this kernel.
-template <int N, bool BIAS, typename Sink>
-__device__ __forceinline__ void ln_epilogue(uint32_t trow, const float* __restrict__ bias,
-                                            const float* __restrict__ gamma, const float* __restrict__ beta, Sink sink)
+// ---- one hidden layer's epilogue: LayerNorm over the N columns of my accumulator row ----------------
+// The accumulator holds x''_j = gamma_j (x_j - mean x) (see the header).  Pass 1: sum of (x''_j / gamma_j)^2
+// -> rstd.  Pass 2: y_j = x''_j rstd + beta_j, handed to sink(chunk, y[32]) BEFORE the ReLU (the sink applies
+// it: for free inside the bf16 conversion for layers 1-2, as FMNMX for the last hidden layer).  All
+// element-wise arithmetic is packed fp32x2 (FMUL2 / FFMA2, new on sm_100).  The TMEM reads are double
+// buffered: chunk c+1 (and pass 2's first chunk) is in flight while chunk c is processed.
+template <int N, typename Sink>
+__device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gamma)[N], const float (&beta)[N], Sink sink)
 {
-    const float2* bias2 = reinterpret_cast<const float2*>(bias);
-    const float2* gamma2 = reinterpret_cast<const float2*>(gamma);
-    const float2* beta2 = reinterpret_cast<const float2*>(beta);
-    float2 s0 = make_float2(0.f, 0.f), s1 = s0, q0 = s0, q1 = s0;       // 4-way ILP on the reductions
-#pragma unroll 1
-    for (int c = 0; c < N / 32; ++c) {
-        float v[32];
-        tmem_ld32(trow + c * 32, v);
+    constexpr int NC = N / 32;
+    static_assert(NC % 2 == 0, "two buffers alternate over an even number of chunks");
+    uint32_t buf[2][32];
+    float2 q[4];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            float2 x0 = make_float2(v[2 * j], v[2 * j + 1]), x1 = make_float2(v[2 * j + 2], v[2 * j + 3]);
-            if (BIAS) { x0 = __fadd2_rn(x0, bias2[c * 16 + j]); x1 = __fadd2_rn(x1, bias2[c * 16 + j + 1]); }
-            s0 = __fadd2_rn(s0, x0); s1 = __fadd2_rn(s1, x1);
-            q0 = __ffma2_rn(x0, x0, q0); q1 = __ffma2_rn(x1, x1, q1);
+    for (int j = 0; j < 4; ++j) q[j] = make_float2(0.f, 0.f);
+    tmem_ld32_issue(trow, buf[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        tmem_ld_wait(buf[c & 1]);
+        tmem_ld32_issue(trow + (uint32_t)(((c + 1) % NC) * 32), buf[(c + 1) & 1]);   // next chunk / pass 2's first
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = c * 32 + 4 * j;              // compile-time after unrolling: c[0][imm] -> uniform registers
+            const float2 t0 = __fmul2_rn(f2_of(buf[c & 1], 2 * j), make_float2(inv_gamma[col], inv_gamma[col + 1]));
+            const float2 t1 = __fmul2_rn(f2_of(buf[c & 1], 2 * j + 1), make_float2(inv_gamma[col + 2], inv_gamma[col + 3]));
+            q[(2 * j) & 3] = __ffma2_rn(t0, t0, q[(2 * j) & 3]);
+            q[(2 * j + 1) & 3] = __ffma2_rn(t1, t1, q[(2 * j + 1) & 3]);
         }
     }
-    const float sum = (s0.x + s0.y) + (s1.x + s1.y), sq = (q0.x + q0.y) + (q1.x + q1.y);
-    const float mean = sum * (1.0f / N);
-    const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / N)), 0.f);      // biased, like nn.LayerNorm
-    const float rstd = rsqrtf(var + 1e-5f);
-    const float2 r2 = make_float2(rstd, rstd), m2 = make_float2(-mean * rstd, -mean * rstd);
-#pragma unroll 1
-    for (int c = 0; c < N / 32; ++c) {
-        float v[32];
-        tmem_ld32(trow + c * 32, v);
+    const float sq = ((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y));
+    const float rstd = rsqrtf(fmaf(sq, 1.0f / N, 1e-5f));                  // biased variance, like nn.LayerNorm
+    const float2 r2 = make_float2(rstd, rstd);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float2 x = make_float2(v[2 * j], v[2 * j + 1]);
-            if (BIAS) x = __fadd2_rn(x, bias2[c * 16 + j]);
-            const float2 nrm = __ffma2_rn(x, r2, m2);                      // (x - mean) * rstd
-            const float2 y = __ffma2_rn(nrm, gamma2[c * 16 + j], beta2[c * 16 + j]);
-            v[2 * j] = y.x; v[2 * j + 1] = y.y;
+    for (int c = 0; c < NC; ++c) {
+        tmem_ld_wait(buf[c & 1]);
+        if (c + 1 < NC) tmem_ld32_issue(trow + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = c * 32 + 4 * j;
+            const float2 y0 = __ffma2_rn(f2_of(buf[c & 1], 2 * j), r2, make_float2(beta[col], beta[col + 1]));
+            const float2 y1 = __ffma2_rn(f2_of(buf[c & 1], 2 * j + 1), r2, make_float2(beta[col + 2], beta[col + 3]));
+            y[4 * j] = y0.x; y[4 * j + 1] = y0.y; y[4 * j + 2] = y1.x; y[4 * j + 3] = y1.y;
         }
-        sink(c, v);
+        sink(c, y);
     }
 }
 
@@ -217,13 +246,18 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     uint8_t* s_a = smem + kSmemA + g * kABytes;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);          // [kGroups]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 40);
-    const float* s_par = reinterpret_cast<const float*>(s_blob + kParOff);
+    const DDPolicyConsts& pc = pa.pc;
 
     // ---- one-time setup: weights -> smem, mbarriers, TMEM ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(pa.blob);
         uint4* dst = reinterpret_cast<uint4*>(s_blob);
-        for (int j = tid; j < kBlobBytes / 16; j += kPolThreads) dst[j] = __ldg(src + j);
+        for (int j = tid; j < kParOff / 16; j += kPolThreads) dst[j] = __ldg(src + j);   // operand images only
+    }
+    {   // the constant A block that carries the biases: row r = [1, 1, 0 x 14] (K chunk 0), zeros (K chunk 1)
+        uint4* ones = reinterpret_cast<uint4*>(smem + kSmemOnes);
+        for (int j = tid; j < kOnesBytes / 16; j += kPolThreads)
+            ones[j] = j < kTile ? make_uint4(0x3f803f80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
 #pragma unroll
@@ -245,6 +279,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint32_t bar = smem_u32(s_bar + g);
     const uint32_t a_addr = smem_u32(s_a);
     const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
+    const uint32_t w1b_addr = smem_u32(s_blob + kW1bOff), w2b_addr = smem_u32(s_blob + kW2bOff), ones_addr = smem_u32(smem + kSmemOnes);
     uint32_t phase = 0;
 
     // ---- my environment ----
@@ -279,11 +314,6 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < kIn; ++j) ob[j] = live ? pa.obs_in[(size_t)i * kIn + j] : 0.f;
         } else {
             write_obs(e, pflags, speed, dist, k, [&](int j, float v) { ob[j] = v; });
-            if (pa.obs_tn && live) {
-                float* dst = pa.obs_tn + o * kIn;
-#pragma unroll
-                for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
-            }
         }
         ob[15] = 1.0f;
 #pragma unroll
@@ -293,17 +323,29 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             w.z = pack_bf16(ob[8 * q + 4], ob[8 * q + 5]); w.w = pack_bf16(ob[8 * q + 6], ob[8 * q + 7]);
             *reinterpret_cast<uint4*>(s_a + q * (kTile * 16) + row * 16) = w;
         }
-        // ---------------- layer 1: D[128x128] = A0[128x16] * W0^T -------------------------------------
+        // ---------------- layer 1: D[128x128] = A0[128x16] * W0''^T -----------------------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (row == 0) {
             tc_fence_after();
             umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);
             umma_commit(bar);
         }
+        // work that does not depend on the network output runs under the first MMA
+        if (!forward_only && pa.obs_tn && live) {
+            float* dst = pa.obs_tn + o * kIn;
+#pragma unroll
+            for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
+        }
+        U4 rnd = {0u, 0u, 0u, 0u};
+        if (!forward_only && pa.mode != DD_ACTION_THRESHOLD) {
+            rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
+                                (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            pin(rnd.a); pin(rnd.b); pin(rnd.c);
+        }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
-        ln_epilogue<kH1, false>(trow, nullptr, s_par + pG0, s_par + pBe0,
-                                [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
-        // ---------------- layer 2: D[128x128] = A1[128x128] * W1^T ------------------------------------
+        ln_epilogue<kH1>(trow, pc.inv_gamma0, pc.beta0,
+                         [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
+        // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (row == 0) {
             tc_fence_after();
@@ -311,12 +353,13 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < kH1 / 16; ++j)
                 umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
                           umma_desc(w1_addr + j * 2 * (kH2 * 16), kH2 * 16, 128), umma_idesc(128, kH2), j > 0 ? 1u : 0u);
+            umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w1b_addr, kH2 * 16, 128), umma_idesc(128, kH2), 1u);
             umma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
-        ln_epilogue<kH2, true>(trow, s_par + pB1, s_par + pG1, s_par + pBe1,
-                               [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
-        // ---------------- layer 3: D[128x64] = A2[128x128] * W2^T -------------------------------------
+        ln_epilogue<kH2>(trow, pc.inv_gamma1, pc.beta1,
+                         [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
+        // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (row == 0) {
             tc_fence_after();
@@ -324,22 +367,24 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < kH2 / 16; ++j)
                 umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
                           umma_desc(w2_addr + j * 2 * (kH3 * 16), kH3 * 16, 128), umma_idesc(128, kH3), j > 0 ? 1u : 0u);
+            umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3), 1u);
             umma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
-        const float2* w3 = reinterpret_cast<const float2*>(s_par + pW3);
-        ln_epilogue<kH3, true>(trow, s_par + pB2, s_par + pG2, s_par + pBe2, [&](int c, const float (&y)[32]) {
+        ln_epilogue<kH3>(trow, pc.inv_gamma2, pc.beta2, [&](int c, const float (&y)[32]) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 h = make_float2(fmaxf(y[2 * j], 0.f), fmaxf(y[2 * j + 1], 0.f));       // ReLU
-                za = __ffma2_rn(h, w3[0 * (kH3 / 2) + c * 16 + j], za);
-                zb = __ffma2_rn(h, w3[1 * (kH3 / 2) + c * 16 + j], zb);
-                zc = __ffma2_rn(h, w3[2 * (kH3 / 2) + c * 16 + j], zc);
+            for (int j = 0; j < 8; ++j) {
+                const float2 h0 = make_float2(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f));      // ReLU
+                const float2 h1 = make_float2(fmaxf(y[4 * j + 2], 0.f), fmaxf(y[4 * j + 3], 0.f));
+                const int col = c * 32 + 4 * j;
+                za = __ffma2_rn(h0, make_float2(pc.w3[0][col], pc.w3[0][col + 1]), za); za = __ffma2_rn(h1, make_float2(pc.w3[0][col + 2], pc.w3[0][col + 3]), za);
+                zb = __ffma2_rn(h0, make_float2(pc.w3[1][col], pc.w3[1][col + 1]), zb); zb = __ffma2_rn(h1, make_float2(pc.w3[1][col + 2], pc.w3[1][col + 3]), zb);
+                zc = __ffma2_rn(h0, make_float2(pc.w3[2][col], pc.w3[2][col + 1]), zc); zc = __ffma2_rn(h1, make_float2(pc.w3[2][col + 2], pc.w3[2][col + 3]), zc);
             }
         });
-        const float z0 = za.x + za.y + s_par[pB3 + 0], z1 = zb.x + zb.y + s_par[pB3 + 1], z2 = zc.x + zc.y + s_par[pB3 + 2];
+        const float z0 = za.x + za.y + pc.b3[0], z1 = zb.x + zb.y + pc.b3[1], z2 = zc.x + zc.y + pc.b3[2];
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         const float p0 = 1.0f / (1.0f + __expf(-z0)), p1 = 1.0f / (1.0f + __expf(-z1)), p2 = 1.0f / (1.0f + __expf(-z2));
         if (pa.probs_tn && live) {
@@ -354,10 +399,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         if (pa.mode == DD_ACTION_THRESHOLD) {
             act = (p0 > 0.5f ? DD_ACT_MAIN : 0u) | (p1 > 0.5f ? DD_ACT_LEFT : 0u) | (p2 > 0.5f ? DD_ACT_RIGHT : 0u);
         } else {
-            const U4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
-                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-            const float u0 = (float)(r.a >> 8) * (1.0f / 16777216.0f), u1 = (float)(r.b >> 8) * (1.0f / 16777216.0f),
-                        u2 = (float)(r.c >> 8) * (1.0f / 16777216.0f);
+            const float u0 = (float)(rnd.a >> 8) * (1.0f / 16777216.0f), u1 = (float)(rnd.b >> 8) * (1.0f / 16777216.0f),
+                        u2 = (float)(rnd.c >> 8) * (1.0f / 16777216.0f);
             act = (u0 < p0 ? DD_ACT_MAIN : 0u) | (u1 < p1 ? DD_ACT_LEFT : 0u) | (u2 < p2 ? DD_ACT_RIGHT : 0u);
         }
         if (pa.logp_tn) {                                    // Bernoulli(probs).log_prob(a).sum(), probs clamped like torch
@@ -422,25 +465,65 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 }
 
 // ---- fp32 torch parameters -> blob ---------------------------------------------------------------
+// One CTA.  For a layer x = W a + b followed by LayerNorm(gamma, beta) over its N outputs:
+//   image = bf16( gamma_n (W[n][k] - mean_n' W[n'][k]) ),  bias'' = gamma_n (b[n] - mean b)  (bf16 hi + lo),
+//   1/gamma and beta stay fp32.  |gamma| < 1e-12 is replaced by +-1e-12: the pre-activation then differs
+//   from beta by < 1.2e-11 (|normalised value| <= sqrt(N)), far below the bf16 activation rounding.
+__device__ __forceinline__ float gamma_clamped(float g) { return fabsf(g) < kGammaFloor ? copysignf(kGammaFloor, g) : g; }
+__device__ __forceinline__ int img_at(int N, int n, int kk) { return (kk / 8) * (N * 8) + n * 8 + (kk % 8); }   // element index
+
 __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, uint8_t* blob)
 {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    __shared__ float s_mean[129];                          // column means of the current layer; [128] = mean of the bias
+    const int tid = threadIdx.x, nth = blockDim.x;
     __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(blob + kW0Off);
     __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(blob + kW1Off);
+    __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>(blob + kW1bOff);
     __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(blob + kW2Off);
+    __nv_bfloat16* w2b = reinterpret_cast<__nv_bfloat16*>(blob + kW2bOff);
     float* par = reinterpret_cast<float*>(blob + kParOff);
-    auto at = [](int N, int n, int kk) { return (kk / 8) * (N * 8) + n * 8 + (kk % 8); };   // element index in the image
+
+    // layer 0: [W0 | b0] is one [128][16] matrix (obs[15] := 1)
+    auto src0 = [&](int n, int kk) { return kk < kIn ? p.w0[n * kIn + kk] : p.b0[n]; };
+    for (int kk = tid; kk < kInPad; kk += nth) {
+        double m = 0.0;
+        for (int n = 0; n < kH1; ++n) m += (double)src0(n, kk);
+        s_mean[kk] = (float)(m / kH1);
+    }
+    __syncthreads();
     for (int j = tid; j < kH1 * kInPad; j += nth) {
         const int n = j / kInPad, kk = j % kInPad;
-        w0[at(kH1, n, kk)] = __float2bfloat16_rn(kk < kIn ? p.w0[n * kIn + kk] : p.b0[n]);
+        w0[img_at(kH1, n, kk)] = __float2bfloat16_rn(gamma_clamped(p.g0[n]) * (src0(n, kk) - s_mean[kk]));
     }
-    for (int j = tid; j < kH2 * kH1; j += nth) { const int n = j / kH1, kk = j % kH1; w1[at(kH2, n, kk)] = __float2bfloat16_rn(p.w1[j]); }
-    for (int j = tid; j < kH3 * kH2; j += nth) { const int n = j / kH2, kk = j % kH2; w2[at(kH3, n, kk)] = __float2bfloat16_rn(p.w2[j]); }
+    __syncthreads();
+    // layers 1, 2: K = 128 weight image + the bias block
+    auto hidden = [&](const float* w, const float* b, const float* g, int N, __nv_bfloat16* img, __nv_bfloat16* bimg) {
+        for (int kk = tid; kk <= 128; kk += nth) {
+            double m = 0.0;
+            for (int n = 0; n < N; ++n) m += (double)(kk < 128 ? w[n * 128 + kk] : b[n]);
+            s_mean[kk] = (float)(m / N);
+        }
+        __syncthreads();
+        for (int j = tid; j < N * 128; j += nth) {
+            const int n = j / 128, kk = j % 128;
+            img[img_at(N, n, kk)] = __float2bfloat16_rn(gamma_clamped(g[n]) * (w[j] - s_mean[kk]));
+        }
+        for (int j = tid; j < N * 16; j += nth) {
+            const int n = j / 16, kk = j % 16;
+            const float v = gamma_clamped(g[n]) * (b[n] - s_mean[128]);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            bimg[img_at(N, n, kk)] = kk == 0 ? hi : (kk == 1 ? lo : __float2bfloat16_rn(0.f));
+        }
+        __syncthreads();
+    };
+    hidden(p.w1, p.b1, p.g1, kH2, w1, w1b);
+    hidden(p.w2, p.b2, p.g2, kH3, w2, w2b);
     for (int j = tid; j < 128; j += nth) {
-        par[pG0 + j] = p.g0[j]; par[pBe0 + j] = p.be0[j];
-        par[pB1 + j] = p.b1[j]; par[pG1 + j] = p.g1[j]; par[pBe1 + j] = p.be1[j];
+        par[pIg0 + j] = 1.0f / gamma_clamped(p.g0[j]); par[pBe0 + j] = p.be0[j];
+        par[pIg1 + j] = 1.0f / gamma_clamped(p.g1[j]); par[pBe1 + j] = p.be1[j];
     }
-    for (int j = tid; j < 64; j += nth) { par[pB2 + j] = p.b2[j]; par[pG2 + j] = p.g2[j]; par[pBe2 + j] = p.be2[j]; }
+    for (int j = tid; j < 64; j += nth) { par[pIg2 + j] = 1.0f / gamma_clamped(p.g2[j]); par[pBe2 + j] = p.be2[j]; }
     for (int j = tid; j < kOut * kH3; j += nth) par[pW3 + j] = p.w3[j];
     for (int j = tid; j < 4; j += nth) par[pB3 + j] = j < kOut ? p.b3[j] : 0.f;
 }
@@ -466,34 +549,39 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, cudaStream_t s
 
 extern "C" {
 
-int dd_policy_pack(const DDPolicy* p, void* blob, void* stream)
+int dd_policy_pack(const DDPolicy* p, void* blob, DDPolicyConsts* consts, void* stream)
 {
-    if (!p || !blob) return DD_E_NULL;
+    if (!p || !blob || !consts) return DD_E_NULL;
     const float* const* q = reinterpret_cast<const float* const*>(p);
     for (int j = 0; j < 14; ++j) if (!q[j]) return DD_E_NULL;
     if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
-    dd::policy_pack_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(*p, (uint8_t*)blob);
-    return (int)cudaGetLastError();
+    dd::policy_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*p, (uint8_t*)blob);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return (int)err;
+    err = cudaMemcpyAsync(consts, (const uint8_t*)blob + dd::kParOff, sizeof(DDPolicyConsts), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }
 
-int dd_policy_forward(const void* blob, const float* obs, float* probs, int64_t n, void* stream)
+int dd_policy_forward(const void* blob, const DDPolicyConsts* consts, const float* obs, float* probs, int64_t n, void* stream)
 {
-    if (!blob || !obs || !probs) return DD_E_NULL;
+    if (!blob || !consts || !obs || !probs) return DD_E_NULL;
     if (n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
     if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
     if (n == 0) return 0;
     dd::PArgs pa{};
+    pa.pc = *consts;
     pa.a.n = (uint32_t)n;
     pa.blob = (const uint8_t*)blob; pa.T = 1; pa.obs_in = obs; pa.probs_tn = probs;
     DDParams p = dd::kDefaultParams;
     return dd::policy_launch(pa, p, n, (cudaStream_t)stream);
 }
 
-int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob, int32_t mode,
-                      uint32_t t0, int32_t T, uint8_t* actions_tn, float* logp_tn, float* reward_tn, uint8_t* done_tn,
+int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob,
+                      const DDPolicyConsts* consts, int32_t mode, uint32_t t0, int32_t T, uint8_t* actions_tn, float* logp_tn, float* reward_tn, uint8_t* done_tn,
                       float* obs_tn, float* probs_tn, float* shaped_tn, uint64_t* stats, int64_t n, void* stream)
 {
-    if (!s || !p || !c || !blob) return DD_E_NULL;
+    if (!s || !p || !c || !blob || !consts) return DD_E_NULL;
     if (s->dtype != DD_F32) return DD_E_DTYPE;                 // the fused kernel is the fp32 throughput path
     if (mode != DD_ACTION_THRESHOLD && mode != DD_ACTION_SAMPLE) return DD_E_RANGE;
     if (T < 0 || n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
@@ -503,6 +591,7 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     if (shaped_tn && !s->prev_dist && n > 0) return DD_E_NULL;
     if (n == 0 || T == 0) return 0;
     dd::PArgs pa{};
+    pa.pc = *consts;
     pa.a.prev_dist = (float*)s->prev_dist; pa.shaped_tn = shaped_tn;
     pa.a.pos_vel = (float*)s->pos_vel; pa.a.att_fuel = (float*)s->att_fuel; pa.a.platform = (float*)s->platform;
     pa.a.steps = s->steps; pa.a.episode = s->episode; pa.a.flags = s->flags;

@@ -18,7 +18,7 @@ import torch
 from . import _native as nv
 from .env import BatchedDroneEnv
 
-BLOB_BYTES = 57360
+BLOB_BYTES = 62736
 ACTION_THRESHOLD, ACTION_SAMPLE = 0, 1
 _KEYS = ("network.0.weight", "network.0.bias", "network.1.weight", "network.1.bias",
          "network.3.weight", "network.3.bias", "network.4.weight", "network.4.bias",
@@ -29,7 +29,7 @@ _SHAPES = ((128, 15), (128,), (128,), (128,), (128, 128), (128,), (128,), (128,)
 
 
 class PolicyBlob:
-    """Device-resident packed policy (57,360 bytes)."""
+    """Device-resident packed policy (62,736 bytes)."""
 
     def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda"):
         self.device = torch.device(device)
@@ -47,9 +47,11 @@ class PolicyBlob:
             params.append(t)
         self._params = params                              # keep alive until the pack kernel has run
         self.blob = torch.empty(BLOB_BYTES, dtype=torch.uint8, device=self.device)
+        self.consts = nv.DDPolicyConsts()                  # host side: rides in the kernel-argument constant bank
         pol = nv.DDPolicy(*[t.data_ptr() for t in params])
-        nv.check(nv.lib().dd_policy_pack(C.byref(pol), self.blob.data_ptr(),
-                                         torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack")
+        with torch.cuda.device(self.device):
+            nv.check(nv.lib().dd_policy_pack(C.byref(pol), self.blob.data_ptr(), C.byref(self.consts),
+                                             torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack")
 
     @classmethod
     def from_module(cls, module: torch.nn.Module, device="cuda") -> "PolicyBlob":
@@ -62,7 +64,7 @@ def policy_forward(blob: PolicyBlob, obs: torch.Tensor) -> torch.Tensor:
         raise ValueError("obs must be a CUDA float32 tensor of shape [N, 15]")
     obs = obs.contiguous()
     probs = torch.empty(obs.shape[0], 3, dtype=torch.float32, device=obs.device)
-    nv.check(nv.lib().dd_policy_forward(blob.blob.data_ptr(), obs.data_ptr(), probs.data_ptr(), obs.shape[0],
+    nv.check(nv.lib().dd_policy_forward(blob.blob.data_ptr(), C.byref(blob.consts), obs.data_ptr(), probs.data_ptr(), obs.shape[0],
                                         torch.cuda.current_stream(obs.device).cuda_stream), "dd_policy_forward")
     return probs
 
@@ -93,7 +95,7 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
             raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {shape} on {dev}")
     ptr = lambda k: bufs[k].data_ptr() if k in bufs else None
     nv.check(nv.lib().dd_policy_rollout(
-        C.byref(env._state), C.byref(env.params), C.byref(env._cfg), blob.blob.data_ptr(),
+        C.byref(env._state), C.byref(env.params), C.byref(env._cfg), blob.blob.data_ptr(), C.byref(blob.consts),
         ACTION_SAMPLE if sample else ACTION_THRESHOLD, int(t0), int(T), ptr("actions"), ptr("logp"), ptr("reward"),
         ptr("done"), ptr("obs"), ptr("probs"), ptr("shaped"), env.stats_slots.data_ptr() if stats else None, n,
         env._stream()),

@@ -1,7 +1,7 @@
 """K5 -- the fused policy rollout (tcgen05 MLP + env step in one kernel) on the GPU.
 
-Tolerances.  The three dense layers run with bf16 operands and fp32 accumulation, so against the
-notebook's eager fp32 network the logits differ by up to ~6e-2 (measured 0.063 max on the fixture
+Tolerances.  The three dense layers run with bf16 operands (LayerNorm centring and gamma folded into
+the weight images by dd_policy_pack) and fp32 accumulation, so against the notebook's eager fp32 network the logits differ by up to ~6e-2 (measured 0.063 max on the fixture
 batch by a bf16-operand emulation in torch): probabilities are compared with atol 3e-2, and
 thresholded actions may only differ where the fp32 |logit| < 0.15.  Against the bf16-operand
 emulation (same roundings, different summation order) the kernel must agree to 3e-3 -- that is
@@ -42,16 +42,38 @@ def _bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _fold(W, b, g):
+    """dd_policy_pack's operand folding: gamma * (centred over the outputs) weights and bias, and 1/gamma."""
+    gc = torch.where(g.abs() < 1e-12, torch.copysign(torch.full_like(g, 1e-12), g), g)
+    Wc = (W.double() - W.double().mean(0, keepdim=True)).float()
+    bc = (b.double() - b.double().mean()).float()
+    return gc[:, None] * Wc, gc * bc, 1.0 / gc
+
+
+def _hi_lo(v):
+    hi = _bf(v)
+    return hi + _bf(v - hi)
+
+
+def _ln_folded(xpp, ig, be):
+    n = xpp.shape[-1]
+    var = ((xpp * ig) ** 2).sum(-1, keepdim=True) / n
+    return xpp * torch.rsqrt(var + 1e-5) + be
+
+
 def _emulate_bf16(sd, x):
-    """Same operand roundings as the kernel: bf16 inputs / weights / hidden activations (and b0, which
-    rides in the bf16 weight image), fp32 accumulation, fp32 LayerNorm, fp32 last layer."""
-    F = torch.nn.functional
-    h = _bf(x) @ _bf(sd["network.0.weight"]).T + _bf(sd["network.0.bias"])
-    h = torch.relu(F.layer_norm(h, (128,), sd["network.1.weight"], sd["network.1.bias"], 1e-5))
-    h = _bf(h) @ _bf(sd["network.3.weight"]).T + sd["network.3.bias"]
-    h = torch.relu(F.layer_norm(h, (128,), sd["network.4.weight"], sd["network.4.bias"], 1e-5))
-    h = _bf(h) @ _bf(sd["network.6.weight"]).T + sd["network.6.bias"]
-    h = torch.relu(F.layer_norm(h, (64,), sd["network.7.weight"], sd["network.7.bias"], 1e-5))
+    """Same operand roundings as the kernel: LayerNorm centring and gamma folded into bf16 weight images
+    (b0 rides in the image as one bf16, b1/b2 as bf16 hi + lo), bf16 inputs / hidden activations, fp32
+    accumulation, fp32 variance + normalisation, fp32 last layer."""
+    W0, b0, ig0 = _fold(sd["network.0.weight"], sd["network.0.bias"], sd["network.1.weight"])
+    W1, b1, ig1 = _fold(sd["network.3.weight"], sd["network.3.bias"], sd["network.4.weight"])
+    W2, b2, ig2 = _fold(sd["network.6.weight"], sd["network.6.bias"], sd["network.7.weight"])
+    h = _bf(x) @ _bf(W0).T + _bf(b0)
+    h = torch.relu(_ln_folded(h, ig0, sd["network.1.bias"]))
+    h = _bf(h) @ _bf(W1).T + _hi_lo(b1)
+    h = torch.relu(_ln_folded(h, ig1, sd["network.4.bias"]))
+    h = _bf(h) @ _bf(W2).T + _hi_lo(b2)
+    h = torch.relu(_ln_folded(h, ig2, sd["network.7.bias"]))
     return torch.sigmoid(h @ sd["network.9.weight"].T + sd["network.9.bias"])
 
 
@@ -92,6 +114,24 @@ def test_forward_random_weights_ragged_sizes(n):
     assert (probs - emu).abs().max().item() < 5e-3, (probs - emu).abs().max().item()
     with torch.no_grad():
         assert (probs - net(x)).abs().max().item() < 8e-2
+
+
+def test_forward_degenerate_layernorm_gammas(fixture):
+    """gamma is folded into the weight images and divided out again for the variance: zero, tiny, negative
+    and large gammas must still give LayerNorm's result (a zero gamma makes that unit the constant beta)."""
+    d, sd = fixture
+    sd = {k_: v.clone() for k_, v in sd.items()}
+    for key in ("network.1.weight", "network.4.weight", "network.7.weight"):
+        g = sd[key]
+        g[0] = 0.0; g[1] = -0.0; g[2] = 1e-20; g[3] = -3e-15; g[4] = -1.7; g[5] = 250.0; g[6] = 1e-6
+    blob = dd.PolicyBlob(sd, device=DEV)
+    x = torch.from_numpy(d["obs"])
+    probs = dd.policy_forward(blob, x.to(DEV)).cpu()
+    assert torch.isfinite(probs).all()
+    with torch.no_grad():
+        ref = pol.reference_policy(sd)(x)
+    assert (probs - _emulate_bf16(sd, x)).abs().max().item() < 5e-3
+    assert (probs - ref).abs().max().item() < 6e-2
 
 
 def test_rollout_env_half_is_exact_and_buffers_are_consistent(fixture):
@@ -165,5 +205,5 @@ def test_policy_argument_errors(fixture):
     with pytest.raises(ValueError):
         dd.PolicyBlob(bad, device=DEV)
     L = nv.lib()
-    assert L.dd_policy_forward(None, None, None, 4, None) == -1
-    assert L.dd_policy_pack(None, None, None) == -1
+    assert L.dd_policy_forward(None, None, None, None, 4, None) == -1
+    assert L.dd_policy_pack(None, None, None, None) == -1
