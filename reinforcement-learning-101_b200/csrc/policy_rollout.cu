@@ -70,7 +70,10 @@ constexpr int kSmemOnes = ((kParOff + 1023) / 1024) * 1024;      // [128][16] bf
 constexpr int kOnesBytes = kTile * 16 * 2;
 constexpr int kSmemA = kSmemOnes + kOnesBytes;
 constexpr int kSmemBar = kSmemA + kGroups * kABytes;
-constexpr int kSmemTotal = kSmemBar + 64;
+constexpr int kObsTileBytes = kTile * kIn * 4;                      // one tile's [128][15] fp32 observations: 7,680 B,
+constexpr int kSmemObs = kSmemBar + 64;                             //   contiguous in obs_tn -> one TMA bulk store
+constexpr int kSmemTotal = kSmemObs + kGroups * kObsTileBytes;      // 225,344 of the 232,448 B
+static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
 
 struct PArgs {
     DDPolicyConsts pc;     // per-column LN parameters + last layer: constant bank -> uniform operands
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
     const uint32_t w1b_addr = smem_u32(s_blob + kW1bOff), w2b_addr = smem_u32(s_blob + kW2bOff), ones_addr = smem_u32(smem + kSmemOnes);
     uint32_t phase = 0;
+    float* s_obs = reinterpret_cast<float*>(smem + kSmemObs + g * kObsTileBytes);
 
     // ---- my environment ----
     const uint32_t tile0 = (blockIdx.x * kGroups + g) * kTile;
@@ -302,6 +306,11 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     float speed = 0.f, dist = 0.f;
     if (!forward_only) speed_dist(e, speed, dist);
     const bool shaping = pa.shaped_tn != nullptr;
+    // The tile's observations of one step are 128 x 15 contiguous floats of obs_tn: full, 16-byte aligned tiles
+    // are staged in shared memory (stride 15 words: conflict-free) and leave with one cp.async.bulk per step.
+    const bool obs_out = !forward_only && pa.obs_tn != nullptr;
+    const bool obs_bulk = obs_out && tile0 + kTile <= a.n && (a.n & 3u) == 0u &&
+                          (reinterpret_cast<uintptr_t>(pa.obs_tn) & 15u) == 0u;
     float dprev = nan_of<float>(), dcur = dist * k.inv_width;
     if (live && shaping) dprev = a.prev_dist[i];
 
@@ -314,6 +323,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < kIn; ++j) ob[j] = live ? pa.obs_in[(size_t)i * kIn + j] : 0.f;
         } else {
             write_obs(e, pflags, speed, dist, k, [&](int j, float v) { ob[j] = v; });
+            if (obs_bulk) {
+#pragma unroll
+                for (int j = 0; j < kIn; ++j) s_obs[row * kIn + j] = ob[j];
+            }
         }
         ob[15] = 1.0f;
 #pragma unroll
@@ -329,9 +342,14 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             tc_fence_after();
             umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);
             umma_commit(bar);
+            if (obs_bulk) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(pa.obs_tn + ((size_t)t * a.n + tile0) * kIn), "r"(smem_u32(s_obs)), "n"(kObsTileBytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
         // work that does not depend on the network output runs under the first MMA
-        if (!forward_only && pa.obs_tn && live) {
+        if (obs_out && !obs_bulk && live) {
             float* dst = pa.obs_tn + o * kIn;
 #pragma unroll
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
@@ -346,6 +364,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         ln_epilogue<kH1>(trow, pc.inv_gamma0, pc.beta0,
                          [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
+        if (obs_bulk && row == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (row == 0) {
             tc_fence_after();
@@ -455,6 +474,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         if (platform_dirty) store2(a.platform, i, e.px, e.py);
         if (shaping) a.prev_dist[i] = dprev;
     }
+    if (obs_bulk && row == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     // ---- teardown: everyone is done with TMEM, then the allocating warp frees it ----
     tc_fence_before();
     __syncthreads();
