@@ -13,7 +13,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libdrone_b200.so")
+# DRONE_B200_LIB selects another in-tree build of the same sources (A/B runs of kernel variants on one box)
+LIB_PATH = os.environ.get("DRONE_B200_LIB") or os.path.join(_HERE, "libdrone_b200.so")
 SOURCES = ("drone_kernels.cu", "ppo_kernels.cu", "policy_rollout.cu")
 NVCC_FLAGS = (
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -188,16 +188,21 @@ struct Env {
 // landing test pays for sin/cos only when the cheap necessary conditions hold (rare); the speed
 // limit is tested on vx^2+vy^2 against a pre-rounded threshold, so the step-only path has a
 // single square root.  Every decision is the reference's, bit for bit, in R arithmetic.
-template <typename R, bool WANT_SPEED>
-DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward, R& speed, R& dist)
+//
+// PRE_SC: the caller already holds (s_pre, c_pre) = sincos_deg(e.angle) of the PRE-update angle -- it does not
+// depend on the action, so the fused policy kernel evaluates it while the network runs.  Same function of
+// the same input: results are bit-identical to the PRE_SC = false instantiation.
+template <typename R, bool WANT_SPEED, bool PRE_SC = false>
+DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward, R& speed, R& dist,
+                         R s_pre = (R)0, R c_pre = (R)0)
 {
     using A = Arith<R>;
     R vx = e.vx, vy = e.vy, w = e.angvel, fuel = e.fuel;
 
     // --- apply_thrust, drone.py:58-76: fuel re-tested before every thruster ------------
     if ((act & DD_ACT_MAIN) && fuel > (R)0) {
-        R s, c;
-        A::sincos_deg(e.angle, s, c);                      // pre-update angle
+        R s = s_pre, c = c_pre;
+        if (!PRE_SC) A::sincos_deg(e.angle, s, c);         // pre-update angle
         vx = A::fma_(k.main_thrust, s, vx);                // 0*c - (-0.6)*s    physics.py:20
         vy = A::fma_(-k.main_thrust, c, vy);               // 0*s + (-0.6)*c    physics.py:21
         fuel -= k.fuel_main;

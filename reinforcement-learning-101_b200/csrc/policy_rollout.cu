@@ -62,7 +62,11 @@ constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 62,736
 static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
 static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
 static_assert(sizeof(DDPolicyConsts) == kParFloats * 4, "the blob's fp32 section is a DDPolicyConsts image");
-constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this is treated as +-1e-12
+constexpr float kGammaFloor = 1e-12f;
+#ifndef DD_K5_CHUNK
+#define DD_K5_CHUNK 16
+#endif
+constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (16 or 32)                      // |gamma| below this is treated as +-1e-12
 
 constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
 constexpr int kSmemBlob = 0;
@@ -139,32 +143,53 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane.  Issue and wait are split so the next chunk
-// can be in flight while this one is processed.  `tcgen05.wait::ld` covers every load the thread has
+// CH (16 or 32) consecutive fp32 columns of this thread's TMEM lane.  Issue and wait are split so the next
+// chunk can be in flight while this one is processed.  `tcgen05.wait::ld` covers every load the thread has
 // issued; the registers are threaded through the wait statements as in/out operands so the compiler
 // cannot schedule a consumer above the wait.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-    asm volatile(""
-                 : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :: "memory");
-}
-__device__ __forceinline__ float2 f2_of(const uint32_t (&r)[32], int pair) {
-    return make_float2(__uint_as_float(r[2 * pair]), __uint_as_float(r[2 * pair + 1]));
+template <int CH> struct TmemChunk;
+template <> struct TmemChunk<16> {
+    uint32_t r[16];
+    __device__ __forceinline__ void issue(uint32_t taddr) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr) : "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                     :: "memory");
+    }
+};
+template <> struct TmemChunk<32> {
+    uint32_t r[32];
+    __device__ __forceinline__ void issue(uint32_t taddr) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr) : "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                     :: "memory");
+        asm volatile(""
+                     : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                       "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                     :: "memory");
+    }
+};
+template <int CH>
+__device__ __forceinline__ float2 f2_of(const TmemChunk<CH>& t, int pair) {
+    return make_float2(__uint_as_float(t.r[2 * pair]), __uint_as_float(t.r[2 * pair + 1]));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);    // .x = lo (low 16 bits)
@@ -183,23 +208,23 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 // it: for free inside the bf16 conversion for layers 1-2, as FMNMX for the last hidden layer).  All
 // element-wise arithmetic is packed fp32x2 (FMUL2 / FFMA2, new on sm_100).  The TMEM reads are double
 // buffered: chunk c+1 (and pass 2's first chunk) is in flight while chunk c is processed.
-template <int N, typename Sink>
+template <int N, int CH, typename Sink>
 __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gamma)[N], const float (&beta)[N], Sink sink)
 {
-    constexpr int NC = N / 32;
+    constexpr int NC = N / CH;
     static_assert(NC % 2 == 0, "two buffers alternate over an even number of chunks");
-    uint32_t buf[2][32];
+    TmemChunk<CH> buf[2];
     float2 q[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) q[j] = make_float2(0.f, 0.f);
-    tmem_ld32_issue(trow, buf[0]);
+    buf[0].issue(trow);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        tmem_ld_wait(buf[c & 1]);
-        tmem_ld32_issue(trow + (uint32_t)(((c + 1) % NC) * 32), buf[(c + 1) & 1]);   // next chunk / pass 2's first
+        buf[c & 1].wait();
+        buf[(c + 1) & 1].issue(trow + (uint32_t)(((c + 1) % NC) * CH));      // next chunk / pass 2's first
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = c * 32 + 4 * j;              // compile-time after unrolling: c[0][imm] -> uniform registers
+        for (int j = 0; j < CH / 4; ++j) {
+            const int col = c * CH + 4 * j;              // compile-time after unrolling: c[0][imm] -> uniform registers
             const float2 t0 = __fmul2_rn(f2_of(buf[c & 1], 2 * j), make_float2(inv_gamma[col], inv_gamma[col + 1]));
             const float2 t1 = __fmul2_rn(f2_of(buf[c & 1], 2 * j + 1), make_float2(inv_gamma[col + 2], inv_gamma[col + 3]));
             q[(2 * j) & 3] = __ffma2_rn(t0, t0, q[(2 * j) & 3]);
@@ -211,12 +236,12 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gam
     const float2 r2 = make_float2(rstd, rstd);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        tmem_ld_wait(buf[c & 1]);
-        if (c + 1 < NC) tmem_ld32_issue(trow + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
-        float y[32];
+        buf[c & 1].wait();
+        if (c + 1 < NC) buf[(c + 1) & 1].issue(trow + (uint32_t)((c + 1) * CH));
+        float y[CH];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = c * 32 + 4 * j;
+        for (int j = 0; j < CH / 4; ++j) {
+            const int col = c * CH + 4 * j;
             const float2 y0 = __ffma2_rn(f2_of(buf[c & 1], 2 * j), r2, make_float2(beta[col], beta[col + 1]));
             const float2 y1 = __ffma2_rn(f2_of(buf[c & 1], 2 * j + 1), r2, make_float2(beta[col + 2], beta[col + 3]));
             y[4 * j] = y0.x; y[4 * j + 1] = y0.y; y[4 * j + 2] = y1.x; y[4 * j + 3] = y1.y;
@@ -225,19 +250,20 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gam
     }
 }
 
-// ReLU + write 32 activations of my row (K columns 32c..32c+31) as bf16 into the A tile (UMMA layout)
-__device__ __forceinline__ void store_a_chunk32_relu(uint8_t* a_tile, int row, int c, const float (&y)[32]) {
+// ReLU + write CH activations of my row (K columns CH*c .. CH*c+CH-1) as bf16 into the A tile (UMMA layout)
+template <int CH>
+__device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int c, const float (&y)[CH]) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {                           // four 16-byte K chunks
+    for (int q = 0; q < CH / 8; ++q) {                      // 16-byte K chunks
         uint4 w;
         w.x = pack_bf16_relu(y[8 * q + 0], y[8 * q + 1]); w.y = pack_bf16_relu(y[8 * q + 2], y[8 * q + 3]);
         w.z = pack_bf16_relu(y[8 * q + 4], y[8 * q + 5]); w.w = pack_bf16_relu(y[8 * q + 6], y[8 * q + 7]);
-        *reinterpret_cast<uint4*>(a_tile + (4 * c + q) * (kTile * 16) + row * 16) = w;
+        *reinterpret_cast<uint4*>(a_tile + ((CH / 8) * c + q) * (kTile * 16) + row * 16) = w;
     }
 }
 
 // =================================================================================================
-template <bool DEF>
+template <bool DEF, int CH>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -280,6 +306,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint32_t tmem_d = tmem_base + (uint32_t)(g * 128);                         // my tile's accumulator columns
     const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);              // my warp's 32 lanes
     const uint32_t bar = smem_u32(s_bar + g);
+    const bool issuer = row == 32 * g;      // tile g issues from its warp g: one issuing warp per scheduler
     const uint32_t a_addr = smem_u32(s_a);
     const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
     const uint32_t w1b_addr = smem_u32(s_blob + kW1bOff), w2b_addr = smem_u32(s_blob + kW2bOff), ones_addr = smem_u32(smem + kSmemOnes);
@@ -338,7 +365,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         }
         // ---------------- layer 1: D[128x128] = A0[128x16] * W0''^T -----------------------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
-        if (row == 0) {
+        if (issuer) {
             tc_fence_after();
             umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);
             umma_commit(bar);
@@ -354,6 +381,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
         }
+        float s_pre = 0.f, c_pre = 1.f;                      // sin / cos of the pre-update angle (main thrust, drone.py:58-66)
+        if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }
         U4 rnd = {0u, 0u, 0u, 0u};
         if (!forward_only && pa.mode != DD_ACTION_THRESHOLD) {
             rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
@@ -361,12 +390,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             pin(rnd.a); pin(rnd.b); pin(rnd.c);
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
-        ln_epilogue<kH1>(trow, pc.inv_gamma0, pc.beta0,
-                         [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
+        ln_epilogue<kH1, CH>(trow, pc.inv_gamma0, pc.beta0,
+                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
-        if (obs_bulk && row == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
+        if (obs_bulk && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         fence_async_smem(); tc_fence_before(); group_bar(g);
-        if (row == 0) {
+        if (issuer) {
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kH1 / 16; ++j)
@@ -376,11 +405,11 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
-        ln_epilogue<kH2>(trow, pc.inv_gamma1, pc.beta1,
-                         [&](int c, const float (&y)[32]) { store_a_chunk32_relu(s_a, row, c, y); });
+        ln_epilogue<kH2, CH>(trow, pc.inv_gamma1, pc.beta1,
+                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
-        if (row == 0) {
+        if (issuer) {
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kH2 / 16; ++j)
@@ -392,12 +421,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
-        ln_epilogue<kH3>(trow, pc.inv_gamma2, pc.beta2, [&](int c, const float (&y)[32]) {
+        ln_epilogue<kH3, CH>(trow, pc.inv_gamma2, pc.beta2, [&](int c, const float (&y)[CH]) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CH / 4; ++j) {
                 const float2 h0 = make_float2(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f));      // ReLU
                 const float2 h1 = make_float2(fmaxf(y[4 * j + 2], 0.f), fmaxf(y[4 * j + 3], 0.f));
-                const int col = c * 32 + 4 * j;
+                const int col = c * CH + 4 * j;
                 za = __ffma2_rn(h0, make_float2(pc.w3[0][col], pc.w3[0][col + 1]), za); za = __ffma2_rn(h1, make_float2(pc.w3[0][col + 2], pc.w3[0][col + 3]), za);
                 zb = __ffma2_rn(h0, make_float2(pc.w3[1][col], pc.w3[1][col + 1]), zb); zb = __ffma2_rn(h1, make_float2(pc.w3[1][col + 2], pc.w3[1][col + 3]), zb);
                 zc = __ffma2_rn(h0, make_float2(pc.w3[2][col], pc.w3[2][col + 1]), zc); zc = __ffma2_rn(h1, make_float2(pc.w3[2][col + 2], pc.w3[2][col + 3]), zc);
@@ -435,7 +464,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         float reward = 0.f, shaped = 0.f;
         if (live) {
             if (!(pflags & DD_DONE)) {
-                uint32_t f = step_core<float, true>(e, act, k, reward, speed, dist);
+                uint32_t f = step_core<float, true, true>(e, act, k, reward, speed, dist, s_pre, c_pre);
                 if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
                 oflags = f;
                 if (shaping) {
@@ -474,7 +503,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         if (platform_dirty) store2(a.platform, i, e.px, e.py);
         if (shaping) a.prev_dist[i] = dprev;
     }
-    if (obs_bulk && row == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (obs_bulk && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     // ---- teardown: everyone is done with TMEM, then the allocating warp frees it ----
     tc_fence_before();
     __syncthreads();
@@ -558,7 +587,7 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, cudaStream_t s
 {
     const int grid = (int)((n + kTile * kGroups - 1) / (kTile * kGroups));
     const bool def = pol_params_default(p);
-    auto kern = def ? policy_rollout_kernel<true> : policy_rollout_kernel<false>;
+    auto kern = def ? policy_rollout_kernel<true, kChunk> : policy_rollout_kernel<false, kChunk>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (err != cudaSuccess) return (int)err;
     kern<<<grid, kPolThreads, kSmemTotal, st>>>(pa);
