@@ -120,6 +120,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp (the same lane every time for the same mask)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "n"(kTile) : "memory"); }
 
 // UMMA shared-memory matrix descriptor: K-major, no swizzle, 8x16-byte core matrices.
@@ -270,7 +276,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const KArgs<float>& a = pa.a;
     const Consts<float> k = consts_of<float, DEF>(a);
 
-    const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, row = tid & (kTile - 1);
+    // The warp index is made warp-uniform FOR THE COMPILER (shfl from lane 0): everything derived from it --
+    // tile index, TMEM / shared-memory addresses, UMMA descriptors -- then lives in uniform registers and
+    // the MMA issue sequence needs no per-instruction lane election.
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), g = warp >> 2, row = tid & (kTile - 1);
     uint8_t* s_blob = smem + kSmemBlob;
     uint8_t* s_a = smem + kSmemA + g * kABytes;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);          // [kGroups]
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint32_t tmem_d = tmem_base + (uint32_t)(g * 128);                         // my tile's accumulator columns
     const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);              // my warp's 32 lanes
     const uint32_t bar = smem_u32(s_bar + g);
-    const bool issuer = row == 32 * g;      // tile g issues from its warp g: one issuing warp per scheduler
+    const bool issuer_warp = (warp & 3) == g;   // tile g issues from its warp g: one issuing warp per scheduler
     const uint32_t a_addr = smem_u32(s_a);
     const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
     const uint32_t w1b_addr = smem_u32(s_blob + kW1bOff), w2b_addr = smem_u32(s_blob + kW2bOff), ones_addr = smem_u32(smem + kSmemOnes);
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         }
         // ---------------- layer 1: D[128x128] = A0[128x16] * W0''^T -----------------------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
-        if (issuer) {
+        if (issuer_warp && elect_one()) {
             tc_fence_after();
             umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);
             umma_commit(bar);
@@ -393,9 +402,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         ln_epilogue<kH1, CH>(trow, pc.inv_gamma0, pc.beta0,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
-        if (obs_bulk && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
+        if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         fence_async_smem(); tc_fence_before(); group_bar(g);
-        if (issuer) {
+        if (issuer_warp && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kH1 / 16; ++j)
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
-        if (issuer) {
+        if (issuer_warp && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kH2 / 16; ++j)
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         if (platform_dirty) store2(a.platform, i, e.px, e.py);
         if (shaping) a.prev_dist[i] = dprev;
     }
-    if (obs_bulk && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     // ---- teardown: everyone is done with TMEM, then the allocating warp frees it ----
     tc_fence_before();
     __syncthreads();
