@@ -180,6 +180,22 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------
+def _ncu_traffic(n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of step_kernel<float,AUTO,OBS> from the committed
+    ncu capture (profiles/r01_traffic_steady.json; ncu cannot run inside the bench).  Only valid for the
+    launch size it was captured at."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic_steady.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        k = d["kernels"]["void step_kernel<float, 1, 1, 1, 256>(KArgs<T1>)"]
+        if d["algorithmic_bytes_per_launch"]["step_kernel<float,AUTO,OBS>"] != BYTES_GYM * n:
+            return None, f"profiles/r01_traffic_steady.json was captured at another launch size than {n} envs"
+        return k["dram_bytes_per_launch"], "profiles/r01_traffic_steady.json (ncu, steady state, --cache-control none)"
+    except (OSError, KeyError, ValueError):
+        return None, "no ncu capture committed"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -375,6 +391,7 @@ def run_ours(args):
         value = n * K * ws / (ms * 1e-3)
         per_launch_s = ms * 1e-3 / K
         achieved = n * BYTES_GYM / per_launch_s / 1e9
+        traffic, traffic_src = _ncu_traffic(n)
         so_ms = results["step_only"]
         so_achieved = n * BYTES_STEP_ONLY / (so_ms * 1e-3 / K) / 1e9
         line = {
@@ -386,7 +403,8 @@ def run_ours(args):
                              f"({S} x ~{n * 116 >> 20} MiB state+outputs > 126 MB L2)",
                        "launch": f"CUDA graph of {G} step launches, replayed, {C_} parallel chain(s) over independent shards; launch_flags={args.launch_flags:#x}", "parallelism": f"env-sharded x{ws}, no per-step comms"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel<float,AUTO,OBS>", "achieved": achieved, "peak": peak_gbs,
-                         "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_GYM * n, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n},
             "variants": {
                 "step_only": {"value": n * K * ws / (so_ms * 1e-3), "ms_per_step": so_ms / K,
