@@ -342,6 +342,22 @@ def run_ours(args):
               "buffers": "obs[T,N,15] f32, action u8, logp f32, reward f32, done u8 (70 B/env-step)",
               "policy": "drone_policy_v1 (27,651 params), Bernoulli sampling, bf16 tcgen05 MMA / fp32 accumulate",
               "stats": penv.stats(reduce=ws > 1)}
+        # 65,536 envs are 512 tiles of 128 = 128 CTAs: 20 of the 148 SMs idle.  One tile set per SM for reference.
+        NF = 148 * 512
+        fenv = dd.BatchedDroneEnv(NF, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                                  max_steps=MAX_STEPS, auto_reset=True, dtype=torch.float32, env_id_base=rank * NF)
+        fenv.reset()
+        fbuf = dd.policy_rollout(fenv, blob, TP, sample=True, want="arldo")
+
+        def run_policy_full(kk):
+            for j in range(kk):
+                dd.policy_rollout(fenv, blob, TP, sample=True, t0=j * TP, want="arldo", out=fbuf)
+        ms_full = timed(lambda: run_policy_full(1), lambda: run_policy_full(reps_p))
+        launches += reps_p
+        k5["all_148_sms"] = {"envs_per_gpu": NF, "ms_per_launch": ms_full / reps_p,
+                             "value": NF * TP * reps_p * ws / (ms_full * 1e-3),
+                             "mlp_tflops": NF * TP * reps_p / (ms_full * 1e-3) * FLOP_STEP / 1e12}
+        del fenv, fbuf
 
     # ---- BASELINE configs[4]: curriculum sweep 75 -> 250, 2M envs per GPU, stats all-reduced over ranks ----
     cur = None

@@ -112,10 +112,14 @@ template <> __device__ __forceinline__ float nan_of<float>() { return __int_as_f
 template <> __device__ __forceinline__ double nan_of<double>() { return __longlong_as_double(0x7ff8000000000000ll); }
 
 __device__ __forceinline__ long long return_fx(double ret) { return __double2ll_rn(ret * DD_RETURN_FIXED_SCALE); }
+// fp32 state: scaling by 2^20 is exact in float, so this is the same integer as the double path, without
+// touching the (slow on B200) FP64 pipe
+__device__ __forceinline__ long long return_fx(float ret) { return __float2ll_rn(ret * (float)DD_RETURN_FIXED_SCALE); }
 
 // Called by ALL 32 lanes of a warp (f == 0 in lanes whose episode goes on).  Costs one ballot in
 // the common case; the reductions and the REDs run only in warps where some episode ended.
-__device__ __forceinline__ void stats_warp_commit(unsigned long long* stats, uint32_t f, double ret, int32_t steps) {
+template <typename R>
+__device__ __forceinline__ void stats_warp_commit(unsigned long long* stats, uint32_t f, R ret, int32_t steps) {
     const unsigned done = __ballot_sync(0xffffffffu, f != 0u);
     if (done == 0u) return;                                // warp-uniform
     const unsigned landed = __ballot_sync(0xffffffffu, (f & DD_LANDED) != 0u);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ KAr
     const bool live = i < a.n;
 
     pdl_wait();                                            // state / actions may come from the previous launch
-    uint32_t f_stat = 0; double ret_stat = 0.0; int32_t len_stat = 0;
+    uint32_t f_stat = 0; R ret_stat = 0; int32_t len_stat = 0;
     if (live) {
         // ---- every load of this thread, back to back ----
         Env<R> e;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ KAr
             if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
             oflags = f;
             if (f) {                                           // rare: ~1 % of env-steps
-                f_stat = f; ret_stat = (double)e.ret; len_stat = e.steps;
+                f_stat = f; ret_stat = e.ret; len_stat = e.steps;
                 if (a.final_obs) {                             // terminal observation (scattered rows)
                     R* fo = a.final_obs + (size_t)i * a.obs_stride;
                     if (!OBS) speed = Arith<R>::sqrt_(Arith<R>::fma_(e.vx, e.vx, Arith<R>::mul(e.vy, e.vy)));
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
 
     for (int32_t t = 0; t < ra.T; ++t) {
         uint32_t oflags = pflags, f_stat = 0;
-        double ret_stat = 0.0; int32_t len_stat = 0;
+        R ret_stat = 0; int32_t len_stat = 0;
         R reward = (R)0, speed = (R)0, dist = (R)0, shaped = (R)0;
         if (live) {
             const size_t o = (size_t)t * a.n + i;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                     dcur = Arith<R>::div(dist, k.width, k.inv_width);
                 }
                 if (f) {
-                    f_stat = f; ret_stat = (double)e.ret; len_stat = e.steps;
+                    f_stat = f; ret_stat = e.ret; len_stat = e.steps;
                     if (ra.auto_reset) {
                         spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
                         ep += 1;

@@ -154,6 +154,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // issued; the registers are threaded through the wait statements as in/out operands so the compiler
 // cannot schedule a consumer above the wait.
 template <int CH> struct TmemChunk;
+template <> struct TmemChunk<8> {
+    uint32_t r[8];
+    __device__ __forceinline__ void issue(uint32_t taddr) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr) : "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+    }
+};
 template <> struct TmemChunk<16> {
     uint32_t r[16];
     __device__ __forceinline__ void issue(uint32_t taddr) {
@@ -344,6 +356,11 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const bool shaping = pa.shaped_tn != nullptr;
     // The tile's observations of one step are 128 x 15 contiguous floats of obs_tn: full, 16-byte aligned tiles
     // are staged in shared memory (stride 15 words: conflict-free) and leave with one cp.async.bulk per step.
+    // launch-constant switches, read from the argument block once
+    const bool out_act = pa.actions_tn != nullptr, out_logp = pa.logp_tn != nullptr, out_rew = pa.reward_tn != nullptr,
+               out_done = pa.done_tn != nullptr, out_probs = pa.probs_tn != nullptr, do_stats = a.stats != nullptr,
+               auto_reset = pa.auto_reset != 0, thresholded = pa.mode == DD_ACTION_THRESHOLD;
+    const int32_t max_steps = a.max_steps;
     const bool obs_out = !forward_only && pa.obs_tn != nullptr;
     const bool obs_bulk = obs_out && tile0 + kTile <= a.n && (a.n & 3u) == 0u &&
                           (reinterpret_cast<uintptr_t>(pa.obs_tn) & 15u) == 0u;
@@ -393,7 +410,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         float s_pre = 0.f, c_pre = 1.f;                      // sin / cos of the pre-update angle (main thrust, drone.py:58-66)
         if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }
         U4 rnd = {0u, 0u, 0u, 0u};
-        if (!forward_only && pa.mode != DD_ACTION_THRESHOLD) {
+        if (!forward_only && !thresholded) {
             rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
                                 (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             pin(rnd.a); pin(rnd.b); pin(rnd.c);
@@ -444,7 +461,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         const float z0 = za.x + za.y + pc.b3[0], z1 = zb.x + zb.y + pc.b3[1], z2 = zc.x + zc.y + pc.b3[2];
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         const float p0 = 1.0f / (1.0f + __expf(-z0)), p1 = 1.0f / (1.0f + __expf(-z1)), p2 = 1.0f / (1.0f + __expf(-z2));
-        if (pa.probs_tn && live) {
+        if (out_probs && live) {
             float* dst = pa.probs_tn + o * kOut;
             dst[0] = p0; dst[1] = p1; dst[2] = p2;
         }
@@ -453,14 +470,14 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         // ---------------- action: threshold (c18:L24-25) or Bernoulli sample (c16:L61-63) --------------
         uint32_t act;
         float logp = 0.f;
-        if (pa.mode == DD_ACTION_THRESHOLD) {
+        if (thresholded) {
             act = (p0 > 0.5f ? DD_ACT_MAIN : 0u) | (p1 > 0.5f ? DD_ACT_LEFT : 0u) | (p2 > 0.5f ? DD_ACT_RIGHT : 0u);
         } else {
             const float u0 = (float)(rnd.a >> 8) * (1.0f / 16777216.0f), u1 = (float)(rnd.b >> 8) * (1.0f / 16777216.0f),
                         u2 = (float)(rnd.c >> 8) * (1.0f / 16777216.0f);
             act = (u0 < p0 ? DD_ACT_MAIN : 0u) | (u1 < p1 ? DD_ACT_LEFT : 0u) | (u2 < p2 ? DD_ACT_RIGHT : 0u);
         }
-        if (pa.logp_tn) {                                    // Bernoulli(probs).log_prob(a).sum(), probs clamped like torch
+        if (out_logp) {                                      // Bernoulli(probs).log_prob(a).sum(), probs clamped like torch
             const float eps = 1.1920929e-07f;
             const float q0 = fminf(fmaxf(p0, eps), 1.f - eps), q1 = fminf(fmaxf(p1, eps), 1.f - eps), q2 = fminf(fmaxf(p2, eps), 1.f - eps);
             logp = __logf((act & DD_ACT_MAIN) ? q0 : 1.f - q0) + __logf((act & DD_ACT_LEFT) ? q1 : 1.f - q1) +
@@ -469,21 +486,21 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 
         // ---------------- environment step (same code as K1) -------------------------------------------
         uint32_t oflags = pflags, f_stat = 0;
-        double ret_stat = 0.0; int32_t len_stat = 0;
+        float ret_stat = 0; int32_t len_stat = 0;
         float reward = 0.f, shaped = 0.f;
         if (live) {
             if (!(pflags & DD_DONE)) {
                 uint32_t f = step_core<float, true, true>(e, act, k, reward, speed, dist, s_pre, c_pre);
-                if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
+                if (!f && max_steps > 0 && e.steps >= max_steps) f = DD_DONE | DD_TRUNCATED;
                 oflags = f;
                 if (shaping) {
-                    shaped = shaped_reward_ppo(e, f, speed, dist, dprev, a.max_steps > 0 && e.steps >= a.max_steps, k);
+                    shaped = shaped_reward_ppo(e, f, speed, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
                     dprev = dcur;
                     dcur = Arith<float>::div(dist, k.width, k.inv_width);
                 }
                 if (f) {
-                    f_stat = f; ret_stat = (double)e.ret; len_stat = e.steps;
-                    if (pa.auto_reset) {
+                    f_stat = f; ret_stat = e.ret; len_stat = e.steps;
+                    if (auto_reset) {
                         spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
                         ep += 1;
                         platform_dirty = true;
@@ -495,12 +512,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                 pflags = f;
             }
             if (shaping) pa.shaped_tn[o] = shaped;
-            if (pa.actions_tn) pa.actions_tn[o] = (uint8_t)act;
-            if (pa.logp_tn) pa.logp_tn[o] = logp;
-            if (pa.reward_tn) pa.reward_tn[o] = reward;
-            if (pa.done_tn) pa.done_tn[o] = (uint8_t)oflags;
+            if (out_act) pa.actions_tn[o] = (uint8_t)act;
+            if (out_logp) pa.logp_tn[o] = logp;
+            if (out_rew) pa.reward_tn[o] = reward;
+            if (out_done) pa.done_tn[o] = (uint8_t)oflags;
         }
-        if (a.stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
+        if (do_stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
     }
 
     if (live && !forward_only) {
