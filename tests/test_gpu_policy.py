@@ -190,6 +190,59 @@ def test_threshold_rollout_lands_with_the_trained_policy(fixture):
     print("trained policy through the fused kernel:", {k_: s[k_] for k_ in ("episodes", "landing_rate", "mean_return", "mean_length")})
 
 
+def test_full_size_cfg4_properties_and_shard_invariance(fixture):
+    """BASELINE configs[3] at its real size (65,536 envs x 250 steps): conservation laws of the statistics,
+    replay of the chosen actions through dd_rollout (bit-identical rewards / flags / state), and independence of
+    the launch shape -- two shards of N/2 with env_id_base 0 and N/2 give exactly the buffers of one env of N
+    (Philox is keyed by the global env id; the MLP is row-independent)."""
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    n, T = 65536, 250
+    kw = dict(seed=7, randomize_drone=True, randomize_platform=True, max_steps=250, auto_reset=True, dtype=torch.float32)
+    a = dd.BatchedDroneEnv(n, device=DEV, **kw); a.reset()
+    out = dd.policy_rollout(a, blob, T, sample=True, want="arld")
+    s = a.stats()
+    assert s["env_steps"] == n * T
+    assert s["episodes"] == s["landed"] + s["crashed"] + s["truncated"]
+    assert s["episodes"] == int(a.get_state()["episode"].sum().item()) - n
+    assert int((out["done"] != 0).sum().item()) == s["episodes"]
+    assert torch.isfinite(out["logp"]).all() and (out["logp"] <= 0).all()
+    # replay through the plain T-step kernel
+    b = dd.BatchedDroneEnv(n, device=DEV, **kw); b.reset()
+    rew = torch.empty(T, n, device=DEV); don = torch.empty(T, n, dtype=torch.uint8, device=DEV)
+    b.rollout(T, "trace", actions=out["actions"], reward_out=rew, done_out=don)
+    assert torch.equal(out["reward"], rew) and torch.equal(out["done"], don)
+    for k_, v in a.get_state().items():
+        assert _eq(v, b.get_state()[k_]), k_
+    assert a.stats() == b.stats()
+    # two shards == one env
+    h = n // 2
+    parts = []
+    for r in range(2):
+        c = dd.BatchedDroneEnv(h, device=DEV, env_id_base=r * h, **kw); c.reset()
+        parts.append((dd.policy_rollout(c, blob, T, sample=True, want="arld"), c))
+    for key in ("actions", "reward", "logp", "done"):
+        assert torch.equal(torch.cat([parts[0][0][key], parts[1][0][key]], dim=1), out[key]), key
+    tot = {k_: parts[0][1].stats()[k_] + parts[1][1].stats()[k_] for k_ in ("episodes", "landed", "crashed", "truncated", "sum_length", "env_steps")}
+    assert tot == {k_: s[k_] for k_ in tot}
+
+
+@pytest.mark.parametrize("n", [1, 3, 130, 1001])
+def test_rollout_ragged_sizes_use_the_fallback_obs_store(fixture, n):
+    """n not a multiple of 4 (or a partial last tile) cannot use the TMA bulk store of the observation tile:
+    the direct-store path must give the same observations as stepping the plain kernels."""
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    T = 40
+    kw = dict(seed=3, randomize_drone=True, randomize_platform=True, max_steps=30, auto_reset=True, dtype=torch.float32)
+    a = dd.BatchedDroneEnv(n, device=DEV, **kw); a.reset()
+    out = dd.policy_rollout(a, blob, T, sample=True, want="ardo")
+    b = dd.BatchedDroneEnv(n, device=DEV, **kw); first = b.reset().clone()
+    obs = torch.empty(T, n, 15, device=DEV); rew = torch.empty(T, n, device=DEV)
+    b.rollout(T, "trace", actions=out["actions"], reward_out=rew, obs_out=obs)
+    assert torch.equal(out["obs"][0], first) and torch.equal(out["obs"][1:], obs[:-1]) and torch.equal(out["reward"], rew)
+
+
 def test_policy_argument_errors(fixture):
     d, sd = fixture
     blob = dd.PolicyBlob(sd, device=DEV)
