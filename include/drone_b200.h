@@ -198,7 +198,7 @@ typedef struct DDPolicy {
     const float *w3, *b3;                 /* network.9 (Linear 64->3) */
 } DDPolicy;
 
-#define DD_POLICY_BLOB_BYTES 62736        /* device workspace filled by dd_policy_pack */
+#define DD_POLICY_BLOB_BYTES 66832        /* device workspace filled by dd_policy_pack */
 #define DD_ACTION_THRESHOLD 0             /* action = probs > 0.5        (c18:L24-25) */
 #define DD_ACTION_SAMPLE    1             /* action ~ Bernoulli(probs)   (c16:L61-63), Philox */
 
@@ -219,9 +219,17 @@ typedef struct DDPolicyConsts {
  * update. */
 int dd_policy_pack(const DDPolicy *p, void *blob, DDPolicyConsts *consts, void *stream);
 
-/* probs[n][3] = policy(obs[n][15]) through the same tcgen05 path the rollout uses (parity hook). */
+/* probs[n][3] = policy(obs[n][15]) through the same tcgen05 path the rollout uses (parity hook).  Persistent
+ * over the rows: any n up to DD_MAX_ENVS_PER_CALL, e.g. a whole [T*N][15] rollout buffer. */
 int dd_policy_forward(const void *blob, const DDPolicyConsts *consts, const float *obs, float *probs, int64_t n,
                       void *stream);
+
+/* The critic DroneTeacherBoi (Actor_Critic_PPO.ipynb: same trunk as the policy, Linear(64, 1) head, no sigmoid):
+ * p->w3 is [1][64], p->b3 is [1].  values[n] = critic(obs[n][15]) -- what the training loop computes over the stored
+ * states (`values = critic(states_tensor)` + the bootstrap value of the final state) before compute_gae. */
+int dd_value_pack(const DDPolicy *p, void *blob, DDPolicyConsts *consts, void *stream);
+int dd_value_forward(const void *blob, const DDPolicyConsts *consts, const float *obs, float *values, int64_t n,
+                     void *stream);
 
 /* T steps of {observe, policy, act, step} in one launch; DD_F32 state only.  Optional [T][n] outputs:
  * actions (DD_ACT_* bits), logp (sum of the 3 Bernoulli log-probs), reward, done flags, obs [T][n][15],

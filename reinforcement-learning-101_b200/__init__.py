@@ -16,7 +16,8 @@ from .distributed import (allreduce_moments, allreduce_stats, init_from_env, mea
 
 __all__ = ["native", "build_native", "BatchedDroneEnv", "StepInfo", "gae", "advantage_moments",
            "normalize_advantages", "allreduce_stats", "allreduce_moments", "shard_range", "stats_dict",
-           "mean_std_from_moments", "init_from_env", "PolicyBlob", "policy_forward", "policy_rollout",
+           "mean_std_from_moments", "init_from_env", "PolicyBlob", "ValueBlob", "policy_forward", "value_forward",
+           "rollout_values", "policy_rollout",
            "step_schedule", "collect_episodes", "curriculum_sweep"]
 
 
@@ -29,7 +30,7 @@ def __getattr__(name):
     if name in ("gae", "advantage_moments", "normalize_advantages"):
         from . import ppo_ops
         return getattr(ppo_ops, name)
-    if name in ("PolicyBlob", "policy_forward", "policy_rollout"):
+    if name in ("PolicyBlob", "ValueBlob", "policy_forward", "value_forward", "rollout_values", "policy_rollout"):
         from . import policy
         return getattr(policy, name)
     if name in ("step_schedule", "collect_episodes", "curriculum_sweep"):

@@ -152,6 +152,10 @@ def lib():
     L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
     L.dd_policy_forward.restype = C.c_int
     L.dd_policy_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
+    L.dd_value_pack.restype = C.c_int
+    L.dd_value_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
+    L.dd_value_forward.restype = C.c_int
+    L.dd_value_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
     L.dd_policy_rollout.restype = C.c_int
     L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, C.POINTER(DDPolicyConsts), i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     if L.dd_abi_version() != ABI_VERSION:
@@ -175,5 +179,5 @@ def default_params() -> DDParams:
 EXPORTS = (
     "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout", "dd_rollout_shaped",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
-    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout",
+    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward",
 )

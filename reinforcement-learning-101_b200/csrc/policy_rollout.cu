@@ -21,6 +21,10 @@
 //     CUDA cores is  var = 1/N sum_j (x''_j / gamma_j)^2  (pass 1: FMUL2 + FFMA2 per column pair) and
 //     y_j = x''_j * rstd + beta_j  (pass 2: one FFMA2, ReLU inside the bf16 conversion), i.e. 4
 //     instructions per pair instead of 7 and a third of the shared-memory parameter traffic;
+//   * the first layer runs in split-bf16 precision: observation and layer-0 image are hi + lo bf16 pairs and
+//     D = x_hi W_hi + x_hi W_lo + x_lo W_hi (three K = 16 MMAs instead of one, ~16 mantissa bits): the input
+//     rounding was 3/4 of the whole network's bf16 error (positions quantised to 1/512) -- measured on the
+//     reference checkpoints: max logit error 0.090 -> 0.020, critic value error 8.9 -> 2.4 (std 254);
 //   * each thread reads its accumulator row with `tcgen05.ld.32x32b.x32` (SASS LDTM), twice,
 //     double-buffered (chunk c+1 is in flight while chunk c is processed) and writes the next A tile
 //     straight into the UMMA layout;
@@ -49,16 +53,17 @@ constexpr int kH1 = 128, kH2 = 128, kH3 = 64, kIn = 15, kInPad = 16, kOut = 3;
 // ---- parameter blob (device memory, produced by policy_pack_kernel; copied verbatim to smem) ----
 // bf16 operand images in UMMA K-major no-swizzle layout: element (n, k) of a [N][K] matrix sits at
 // byte (k / 8) * (N * 16) + n * 16 + (k % 8) * 2   (8x16-byte core matrices; LBO = N*16, SBO = 128)
-constexpr int kW0Off = 0;                                  // [128][16]  G0 C0 [W0 | b0]  (obs[15] := 1)
+constexpr int kW0Off = 0;                                  // [128][16]  G0 C0 [W0 | b0]  (obs[15] := 1), high halves
 constexpr int kW1Off = kW0Off + kH1 * kInPad * 2;          // [128][128] G1 C1 W1
 constexpr int kW1bOff = kW1Off + kH2 * kH1 * 2;            // [128][16]  col 0/1 = hi/lo of G1 C1 b1
 constexpr int kW2Off = kW1bOff + kH2 * 16 * 2;             // [64][128]  G2 C2 W2
 constexpr int kW2bOff = kW2Off + kH3 * kH2 * 2;            // [64][16]   col 0/1 = hi/lo of G2 C2 b2
-constexpr int kParOff = kW2bOff + kH3 * 16 * 2;            // fp32 parameters
+constexpr int kW0loOff = kW2bOff + kH3 * 16 * 2;           // [128][16]  low halves of the layer-0 image (split bf16)
+constexpr int kParOff = kW0loOff + kH1 * kInPad * 2;       // fp32 parameters
 // fp32 parameter order: 1/gamma and beta per LayerNorm, then the last Linear
 constexpr int pIg0 = 0, pBe0 = 128, pIg1 = 256, pBe1 = 384, pIg2 = 512, pBe2 = 576, pW3 = 640, pB3 = 832,
               kParFloats = 836;
-constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 62,736
+constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 66,832
 static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
 static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
 static_assert(sizeof(DDPolicyConsts) == kParFloats * 4, "the blob's fp32 section is a DDPolicyConsts image");
@@ -75,7 +80,8 @@ constexpr int kOnesBytes = kTile * 16 * 2;
 constexpr int kSmemA = kSmemOnes + kOnesBytes;
 constexpr int kSmemBar = kSmemA + kGroups * kABytes;
 constexpr int kObsTileBytes = kTile * kIn * 4;                      // one tile's [128][15] fp32 observations: 7,680 B,
-constexpr int kSmemObs = kSmemBar + 64;                             //   contiguous in obs_tn -> one TMA bulk store
+constexpr int kSmemObs = kSmemBar + 80;                             //   contiguous in obs_tn -> one TMA bulk store
+                                                                    //   (bar area: 4 MMA + 4 obs-load mbarriers, TMEM base)
 constexpr int kSmemTotal = kSmemObs + kGroups * kObsTileBytes;      // 225,344 of the 232,448 B
 static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
 
@@ -93,8 +99,9 @@ struct PArgs {
     float* obs_tn;             // [T][n][15]
     float* probs_tn;           // [T][n][3] (optional)
     float* shaped_tn;          // [T][n] notebook training reward (optional)
-    const float* obs_in;       // forward-only mode: [n][15], no env stepping
+    const float* obs_in;       // forward-only instantiation: [n][15], no env stepping
     int32_t auto_reset;
+    int32_t head;              // forward-only: 3 = probs[n][3] (sigmoid, DroneGamerBoi), 1 = values[n] (DroneTeacherBoi)
 };
 
 // ---- raw PTX wrappers -----------------------------------------------------------------------
@@ -281,7 +288,11 @@ __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int
 }
 
 // =================================================================================================
-template <bool DEF, int CH>
+// FWD = false: the T-step rollout (a thread owns one environment).  FWD = true: the network alone over n rows of
+// observations (parity hook for the policy; the critic's values over a rollout buffer), persistent over blocks of
+// 512 rows: the "step" loop walks row blocks and the observation tile of the NEXT block is fetched by TMA
+// (cp.async.bulk -> mbarrier) while the current one goes through the layers.
+template <bool DEF, int CH, bool FWD>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -294,9 +305,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), g = warp >> 2, row = tid & (kTile - 1);
     uint8_t* s_blob = smem + kSmemBlob;
     uint8_t* s_a = smem + kSmemA + g * kABytes;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);          // [kGroups]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 40);
-    const DDPolicyConsts& pc = pa.pc;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);          // [kGroups] MMA done, [kGroups] obs tile landed
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 64);
 
     // ---- one-time setup: weights -> smem, mbarriers, TMEM ----
     {
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     }
     if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < kGroups; ++j) mbar_init(smem_u32(s_bar + j), 1);
+        for (int j = 0; j < 2 * kGroups; ++j) mbar_init(smem_u32(s_bar + j), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                        // one warp allocates the whole TMEM (512 columns)
@@ -331,14 +341,27 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint32_t a_addr = smem_u32(s_a);
     const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
     const uint32_t w1b_addr = smem_u32(s_blob + kW1bOff), w2b_addr = smem_u32(s_blob + kW2bOff), ones_addr = smem_u32(smem + kSmemOnes);
+    const uint32_t w0lo_addr = smem_u32(s_blob + kW0loOff);
     uint32_t phase = 0;
     float* s_obs = reinterpret_cast<float*>(smem + kSmemObs + g * kObsTileBytes);
+    const DDPolicyConsts& pc = pa.pc;
 
-    // ---- my environment ----
-    const uint32_t tile0 = (blockIdx.x * kGroups + g) * kTile;
-    const uint32_t i = tile0 + row;
-    const bool live = i < a.n;
-    const bool forward_only = pa.obs_in != nullptr;
+    // ---- my environment (FWD: my row of the current block, advanced in the loop) ----
+    constexpr bool forward_only = FWD;
+    uint32_t tile0 = (blockIdx.x * kGroups + g) * kTile;
+    uint32_t i = tile0 + row;
+    bool live = i < a.n;
+    // FWD: a tile's [128][15] fp32 rows are contiguous: full 16-byte aligned tiles arrive by TMA into s_obs
+    const bool in_aligned = FWD && (reinterpret_cast<uintptr_t>(pa.obs_in) & 15u) == 0u;
+    const uint32_t obs_bar = smem_u32(s_bar + kGroups + g);
+    uint32_t obs_phase = 0;
+    auto tile_bulk_in = [&](uint32_t t0_) { return in_aligned && (uint64_t)t0_ + kTile <= (uint64_t)a.n; };
+    auto fetch_tile = [&](uint32_t t0_) {                    // one elected thread
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(obs_bar), "n"(kObsTileBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(s_obs)), "l"(pa.obs_in + (size_t)t0_ * kIn), "n"(kObsTileBytes), "r"(obs_bar) : "memory");
+    };
+    if (FWD && tile_bulk_in(tile0) && issuer_warp && elect_one()) fetch_tile(tile0);
     Env<float> e = {};
     uint32_t pflags = 0, ep = 0;
     bool platform_dirty = false;
@@ -368,12 +391,19 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     if (live && shaping) dprev = a.prev_dist[i];
 
     for (int32_t t = 0; t < pa.T; ++t) {
-        const size_t o = (size_t)t * a.n + i;
+        const size_t o = FWD ? (size_t)i : (size_t)t * a.n + i;
         // ---------------- observation -> A0 (bf16, K = 16: 15 inputs + constant 1 for the bias) -------
         float ob[16];
+        const bool tile_in = FWD && tile_bulk_in(tile0);     // warp-uniform: this tile's rows are in s_obs (or on their way)
         if (forward_only) {
+            if (tile_in) {
+                mbar_wait(obs_bar, obs_phase); obs_phase ^= 1u;
 #pragma unroll
-            for (int j = 0; j < kIn; ++j) ob[j] = live ? pa.obs_in[(size_t)i * kIn + j] : 0.f;
+                for (int j = 0; j < kIn; ++j) ob[j] = s_obs[row * kIn + j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < kIn; ++j) ob[j] = live ? pa.obs_in[(size_t)i * kIn + j] : 0.f;
+            }
         } else {
             write_obs(e, pflags, speed, dist, k, [&](int j, float v) { ob[j] = v; });
             if (obs_bulk) {
@@ -382,19 +412,31 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             }
         }
         ob[15] = 1.0f;
+        // split bf16: hi = bf16(x), lo = bf16(x - hi); K chunks 0-1 = hi, 2-3 = lo
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            uint4 w;
-            w.x = pack_bf16(ob[8 * q + 0], ob[8 * q + 1]); w.y = pack_bf16(ob[8 * q + 2], ob[8 * q + 3]);
-            w.z = pack_bf16(ob[8 * q + 4], ob[8 * q + 5]); w.w = pack_bf16(ob[8 * q + 6], ob[8 * q + 7]);
-            *reinterpret_cast<uint4*>(s_a + q * (kTile * 16) + row * 16) = w;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = ob[8 * q + 2 * j], x1 = ob[8 * q + 2 * j + 1];
+                hi[j] = pack_bf16(x0, x1);
+                lo[j] = pack_bf16(x0 - __uint_as_float(hi[j] << 16), x1 - __uint_as_float(hi[j] & 0xffff0000u));
+            }
+            *reinterpret_cast<uint4*>(s_a + q * (kTile * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(s_a + (2 + q) * (kTile * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        // ---------------- layer 1: D[128x128] = A0[128x16] * W0''^T -----------------------------------
+        // ---------------- layer 1: D[128x128] = A0[128x16] * W0''^T, split bf16 (3 MMAs) ---------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (issuer_warp && elect_one()) {
             tc_fence_after();
-            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);
+            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);      // x_hi W_hi
+            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0lo_addr, kH1 * 16, 128), umma_idesc(128, kH1), 1u);    // x_hi W_lo
+            umma_bf16(tmem_d, umma_desc(a_addr + 2 * (kTile * 16), kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 1u);   // x_lo W_hi
             umma_commit(bar);
+            if (FWD) {                                       // everyone has read s_obs: fetch the next block's tile
+                const uint32_t next0 = tile0 + gridDim.x * (kGroups * kTile);
+                if (t + 1 < pa.T && tile_bulk_in(next0)) fetch_tile(next0);
+            }
             if (obs_bulk) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(pa.obs_tn + ((size_t)t * a.n + tile0) * kIn), "r"(smem_u32(s_obs)), "n"(kObsTileBytes) : "memory");
@@ -461,11 +503,18 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         const float z0 = za.x + za.y + pc.b3[0], z1 = zb.x + zb.y + pc.b3[1], z2 = zc.x + zc.y + pc.b3[2];
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         const float p0 = 1.0f / (1.0f + __expf(-z0)), p1 = 1.0f / (1.0f + __expf(-z1)), p2 = 1.0f / (1.0f + __expf(-z2));
-        if (out_probs && live) {
+        if (FWD && pa.head == 1) {                           // critic: the raw scalar (DroneTeacherBoi, c12)
+            if (live) pa.probs_tn[o] = z0;
+        } else if (out_probs && live) {
             float* dst = pa.probs_tn + o * kOut;
             dst[0] = p0; dst[1] = p1; dst[2] = p2;
         }
-        if (forward_only) continue;
+        if (forward_only) {                                  // next block of rows
+            tile0 += gridDim.x * (kGroups * kTile);
+            i = tile0 + row;
+            live = i < a.n;
+            continue;
+        }
 
         // ---------------- action: threshold (c18:L24-25) or Bernoulli sample (c16:L61-63) --------------
         uint32_t act;
@@ -547,7 +596,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 __device__ __forceinline__ float gamma_clamped(float g) { return fabsf(g) < kGammaFloor ? copysignf(kGammaFloor, g) : g; }
 __device__ __forceinline__ int img_at(int N, int n, int kk) { return (kk / 8) * (N * 8) + n * 8 + (kk % 8); }   // element index
 
-__global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, uint8_t* blob)
+__global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, int head, uint8_t* blob)
 {
     __shared__ float s_mean[129];                          // column means of the current layer; [128] = mean of the bias
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -556,6 +605,7 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, uint8_t* b
     __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>(blob + kW1bOff);
     __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(blob + kW2Off);
     __nv_bfloat16* w2b = reinterpret_cast<__nv_bfloat16*>(blob + kW2bOff);
+    __nv_bfloat16* w0lo = reinterpret_cast<__nv_bfloat16*>(blob + kW0loOff);
     float* par = reinterpret_cast<float*>(blob + kParOff);
 
     // layer 0: [W0 | b0] is one [128][16] matrix (obs[15] := 1)
@@ -568,7 +618,10 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, uint8_t* b
     __syncthreads();
     for (int j = tid; j < kH1 * kInPad; j += nth) {
         const int n = j / kInPad, kk = j % kInPad;
-        w0[img_at(kH1, n, kk)] = __float2bfloat16_rn(gamma_clamped(p.g0[n]) * (src0(n, kk) - s_mean[kk]));
+        const float v = gamma_clamped(p.g0[n]) * (src0(n, kk) - s_mean[kk]);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        w0[img_at(kH1, n, kk)] = hi;
+        w0lo[img_at(kH1, n, kk)] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
     __syncthreads();
     // layers 1, 2: K = 128 weight image + the bias block
@@ -599,8 +652,8 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, uint8_t* b
         par[pIg1 + j] = 1.0f / gamma_clamped(p.g1[j]); par[pBe1 + j] = p.be1[j];
     }
     for (int j = tid; j < 64; j += nth) { par[pIg2 + j] = 1.0f / gamma_clamped(p.g2[j]); par[pBe2 + j] = p.be2[j]; }
-    for (int j = tid; j < kOut * kH3; j += nth) par[pW3 + j] = p.w3[j];
-    for (int j = tid; j < 4; j += nth) par[pB3 + j] = j < kOut ? p.b3[j] : 0.f;
+    for (int j = tid; j < kOut * kH3; j += nth) par[pW3 + j] = j < head * kH3 ? p.w3[j] : 0.f;   // head rows of [head][64]
+    for (int j = tid; j < 4; j += nth) par[pB3 + j] = j < head ? p.b3[j] : 0.f;
 }
 
 static bool pol_params_default(const DDParams& p)
@@ -609,15 +662,55 @@ static bool pol_params_default(const DDParams& p)
     return memcmp(&p, &d, sizeof d) == 0;
 }
 
-static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, cudaStream_t st)
+static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, cudaStream_t st)
 {
-    const int grid = (int)((n + kTile * kGroups - 1) / (kTile * kGroups));
+    const int blocks = (int)((n + kTile * kGroups - 1) / (kTile * kGroups));
     const bool def = pol_params_default(p);
-    auto kern = def ? policy_rollout_kernel<true, kChunk> : policy_rollout_kernel<false, kChunk>;
+    void (*kern)(PArgs);
+    int grid = blocks;
+    if (forward) {
+        kern = policy_rollout_kernel<true, kChunk, true>;
+        int dev = 0, sms = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        grid = blocks < sms ? blocks : sms;                 // persistent: one CTA per SM walks the row blocks
+        pa.T = (blocks + grid - 1) / grid;
+    } else {
+        kern = def ? policy_rollout_kernel<true, kChunk, false> : policy_rollout_kernel<false, kChunk, false>;
+    }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (err != cudaSuccess) return (int)err;
     kern<<<grid, kPolThreads, kSmemTotal, st>>>(pa);
     return (int)cudaGetLastError();
+}
+
+static int pack_common(const DDPolicy* p, int head, void* blob, DDPolicyConsts* consts, void* stream)
+{
+    if (!p || !blob || !consts) return DD_E_NULL;
+    const float* const* q = reinterpret_cast<const float* const*>(p);
+    for (int j = 0; j < 14; ++j) if (!q[j]) return DD_E_NULL;
+    if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
+    policy_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*p, head, (uint8_t*)blob);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return (int)err;
+    err = cudaMemcpyAsync(consts, (const uint8_t*)blob + kParOff, sizeof(DDPolicyConsts), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
+static int forward_common(const void* blob, const DDPolicyConsts* consts, const float* obs, float* out, int head, int64_t n, void* stream)
+{
+    if (!blob || !consts || !obs || !out) return DD_E_NULL;
+    if (n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
+    if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
+    if (n == 0) return 0;
+    PArgs pa{};
+    pa.pc = *consts;
+    pa.a.n = (uint32_t)n;
+    pa.blob = (const uint8_t*)blob; pa.T = 1; pa.obs_in = obs; pa.probs_tn = out; pa.head = head;
+    DDParams p = kDefaultParams;
+    return policy_launch(pa, p, n, true, (cudaStream_t)stream);
 }
 
 }  // namespace dd
@@ -626,30 +719,22 @@ extern "C" {
 
 int dd_policy_pack(const DDPolicy* p, void* blob, DDPolicyConsts* consts, void* stream)
 {
-    if (!p || !blob || !consts) return DD_E_NULL;
-    const float* const* q = reinterpret_cast<const float* const*>(p);
-    for (int j = 0; j < 14; ++j) if (!q[j]) return DD_E_NULL;
-    if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
-    dd::policy_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*p, (uint8_t*)blob);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return (int)err;
-    err = cudaMemcpyAsync(consts, (const uint8_t*)blob + dd::kParOff, sizeof(DDPolicyConsts), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    if (err != cudaSuccess) return (int)err;
-    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+    return dd::pack_common(p, 3, blob, consts, stream);
+}
+
+int dd_value_pack(const DDPolicy* p, void* blob, DDPolicyConsts* consts, void* stream)
+{
+    return dd::pack_common(p, 1, blob, consts, stream);
 }
 
 int dd_policy_forward(const void* blob, const DDPolicyConsts* consts, const float* obs, float* probs, int64_t n, void* stream)
 {
-    if (!blob || !consts || !obs || !probs) return DD_E_NULL;
-    if (n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
-    if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
-    if (n == 0) return 0;
-    dd::PArgs pa{};
-    pa.pc = *consts;
-    pa.a.n = (uint32_t)n;
-    pa.blob = (const uint8_t*)blob; pa.T = 1; pa.obs_in = obs; pa.probs_tn = probs;
-    DDParams p = dd::kDefaultParams;
-    return dd::policy_launch(pa, p, n, (cudaStream_t)stream);
+    return dd::forward_common(blob, consts, obs, probs, 3, n, stream);
+}
+
+int dd_value_forward(const void* blob, const DDPolicyConsts* consts, const float* obs, float* values, int64_t n, void* stream)
+{
+    return dd::forward_common(blob, consts, obs, values, 1, n, stream);
 }
 
 int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob,
@@ -677,7 +762,7 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     pa.blob = (const uint8_t*)blob; pa.mode = mode; pa.t0 = t0; pa.T = T;
     pa.actions_tn = actions_tn; pa.logp_tn = logp_tn; pa.reward_tn = reward_tn; pa.done_tn = done_tn;
     pa.obs_tn = obs_tn; pa.probs_tn = probs_tn; pa.obs_in = nullptr; pa.auto_reset = c->auto_reset;
-    return dd::policy_launch(pa, *p, n, (cudaStream_t)stream);
+    return dd::policy_launch(pa, *p, n, false, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ import torch
 from . import _native as nv
 from .env import BatchedDroneEnv
 
-BLOB_BYTES = 62736
+BLOB_BYTES = 66832
 ACTION_THRESHOLD, ACTION_SAMPLE = 0, 1
 _KEYS = ("network.0.weight", "network.0.bias", "network.1.weight", "network.1.bias",
          "network.3.weight", "network.3.bias", "network.4.weight", "network.4.bias",
@@ -29,14 +29,20 @@ _SHAPES = ((128, 15), (128,), (128,), (128,), (128, 128), (128,), (128,), (128,)
 
 
 class PolicyBlob:
-    """Device-resident packed policy (62,736 bytes)."""
+    """Device-resident packed network (66,832 bytes) + its host-side per-column constants.
+    ``head=3``: the policy ``DroneGamerBoi`` (sigmoid probabilities); ``head=1``: the critic
+    ``DroneTeacherBoi`` (same trunk, ``Linear(64, 1)``, raw scalar) -- see ``ValueBlob``."""
 
-    def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda"):
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda", head: int = 3):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PolicyBlob lives on a CUDA device")
+        if head not in (1, 3):
+            raise ValueError("head must be 3 (policy) or 1 (critic)")
+        self.head = head
+        shapes = _SHAPES[:-2] + ((head, 64), (head,))
         params = []
-        for key, shape in zip(_KEYS, _SHAPES):
+        for key, shape in zip(_KEYS, shapes):
             if key not in state_dict and key[len("network."):] in state_dict:
                 key = key[len("network."):]                 # a bare nn.Sequential: '0.weight', ...
             if key not in state_dict:
@@ -50,23 +56,61 @@ class PolicyBlob:
         self.consts = nv.DDPolicyConsts()                  # host side: rides in the kernel-argument constant bank
         pol = nv.DDPolicy(*[t.data_ptr() for t in params])
         with torch.cuda.device(self.device):
-            nv.check(nv.lib().dd_policy_pack(C.byref(pol), self.blob.data_ptr(), C.byref(self.consts),
-                                             torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack")
+            pack = nv.lib().dd_policy_pack if head == 3 else nv.lib().dd_value_pack
+            nv.check(pack(C.byref(pol), self.blob.data_ptr(), C.byref(self.consts),
+                          torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack" if head == 3 else "dd_value_pack")
 
     @classmethod
-    def from_module(cls, module: torch.nn.Module, device="cuda") -> "PolicyBlob":
-        return cls(module.state_dict(), device=device)
+    def from_module(cls, module: torch.nn.Module, device="cuda", head: int = 3) -> "PolicyBlob":
+        return cls(module.state_dict(), device=device, head=head)
+
+
+def ValueBlob(state_dict: Mapping[str, torch.Tensor], device="cuda") -> PolicyBlob:
+    """The critic ``DroneTeacherBoi`` (Actor_Critic_PPO.ipynb: 15-128-128-64-1, LayerNorm + ReLU) packed for
+    ``value_forward``."""
+    return PolicyBlob(state_dict, device=device, head=1)
+
+
+def _rows(obs: torch.Tensor) -> torch.Tensor:
+    if not obs.is_cuda or obs.dtype != torch.float32 or obs.dim() < 2 or obs.shape[-1] != 15:
+        raise ValueError("obs must be a CUDA float32 tensor of shape [..., 15]")
+    return obs.contiguous().view(-1, 15)
 
 
 def policy_forward(blob: PolicyBlob, obs: torch.Tensor) -> torch.Tensor:
-    """probs [N,3] = sigmoid(policy(obs [N,15])) on the tensor-core path."""
-    if not obs.is_cuda or obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[1] != 15:
-        raise ValueError("obs must be a CUDA float32 tensor of shape [N, 15]")
-    obs = obs.contiguous()
-    probs = torch.empty(obs.shape[0], 3, dtype=torch.float32, device=obs.device)
-    nv.check(nv.lib().dd_policy_forward(blob.blob.data_ptr(), C.byref(blob.consts), obs.data_ptr(), probs.data_ptr(), obs.shape[0],
+    """probs [..., 3] = sigmoid(policy(obs [..., 15])) on the tensor-core path (persistent over the rows)."""
+    if blob.head != 3:
+        raise ValueError("policy_forward needs a policy blob (head=3)")
+    rows = _rows(obs)
+    probs = torch.empty(rows.shape[0], 3, dtype=torch.float32, device=obs.device)
+    nv.check(nv.lib().dd_policy_forward(blob.blob.data_ptr(), C.byref(blob.consts), rows.data_ptr(), probs.data_ptr(), rows.shape[0],
                                         torch.cuda.current_stream(obs.device).cuda_stream), "dd_policy_forward")
-    return probs
+    return probs.view(*obs.shape[:-1], 3)
+
+
+def value_forward(blob: PolicyBlob, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """values [...] = critic(obs [..., 15]) -- ``values = critic(states_tensor)`` of the PPO training loop
+    (Actor_Critic_PPO.ipynb, PHASE 2) for a whole rollout buffer in one launch."""
+    if blob.head != 1:
+        raise ValueError("value_forward needs a critic blob (ValueBlob / head=1)")
+    rows = _rows(obs)
+    if out is None:
+        out = torch.empty(obs.shape[:-1], dtype=torch.float32, device=obs.device)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != rows.shape[0] or out.device != obs.device:
+        raise ValueError("out must be a contiguous float32 tensor with one element per observation row")
+    nv.check(nv.lib().dd_value_forward(blob.blob.data_ptr(), C.byref(blob.consts), rows.data_ptr(), out.data_ptr(), rows.shape[0],
+                                       torch.cuda.current_stream(obs.device).cuda_stream), "dd_value_forward")
+    return out
+
+
+def rollout_values(vblob: PolicyBlob, obs_tn: torch.Tensor, final_obs: torch.Tensor) -> torch.Tensor:
+    """values [T+1, N] for ``gae``: the critic on the rollout's observations obs_tn [T, N, 15] plus the bootstrap
+    row on the observation after the last step (final_obs [N, 15], e.g. ``env.observe()``)."""
+    T, n = obs_tn.shape[0], obs_tn.shape[1]
+    v = torch.empty(T + 1, n, dtype=torch.float32, device=obs_tn.device)
+    value_forward(vblob, obs_tn, out=v[:T])
+    value_forward(vblob, final_obs, out=v[T])
+    return v
 
 
 def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool = True, t0: int = 0,
@@ -103,12 +147,12 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
     return bufs
 
 
-def reference_policy(state_dict: Mapping[str, torch.Tensor]) -> torch.nn.Module:
-    """An eager fp32 torch module with the notebook's architecture (for tests / comparisons)."""
+def reference_policy(state_dict: Mapping[str, torch.Tensor], head: int = 3) -> torch.nn.Module:
+    """An eager fp32 torch module with the notebook's architecture (for tests / comparisons); head=1: the critic."""
     net = torch.nn.Sequential(
         torch.nn.Linear(15, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
         torch.nn.Linear(128, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
         torch.nn.Linear(128, 64), torch.nn.LayerNorm(64), torch.nn.ReLU(),
-        torch.nn.Linear(64, 3), torch.nn.Sigmoid())
+        *((torch.nn.Linear(64, 3), torch.nn.Sigmoid()) if head == 3 else (torch.nn.Linear(64, 1),)))
     net.load_state_dict({k.replace("network.", ""): v for k, v in state_dict.items()})
     return net

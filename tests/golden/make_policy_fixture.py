@@ -12,6 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/models/actor-critic-ppo/drone_policy_v1.pth"
+SRC_CRITIC = "/root/reference/models/actor-critic-ppo/drone_critic_v1.pth"     # DroneTeacherBoi, same trunk, 1 output
 
 
 def fixed_obs(n=512, seed=1234):
@@ -46,6 +47,21 @@ def main():
     np.savez_compressed(os.path.join(HERE, "policy_v1.npz"), **out)
     print("wrote policy_v1.npz;", sum(v.size for k, v in out.items() if k.startswith("network")), "parameters;",
           "logit range", logits.min(), logits.max())
+    # the critic of the same run: values on the same observation batch
+    sdc = torch.load(SRC_CRITIC, weights_only=True, map_location="cpu")
+    crit = torch.nn.Sequential(
+        torch.nn.Linear(15, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
+        torch.nn.Linear(128, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
+        torch.nn.Linear(128, 64), torch.nn.LayerNorm(64), torch.nn.ReLU(),
+        torch.nn.Linear(64, 1))
+    crit.load_state_dict({k.replace("network.", ""): v for k, v in sdc.items()})
+    with torch.no_grad():
+        values = crit(torch.from_numpy(obs)).squeeze(-1).numpy()
+    outc = {k: v.numpy().astype(np.float32) for k, v in sdc.items()}
+    outc["obs"], outc["values"] = obs, values
+    np.savez_compressed(os.path.join(HERE, "critic_v1.npz"), **outc)
+    print("wrote critic_v1.npz;", sum(v.size for k, v in outc.items() if k.startswith("network")), "parameters;",
+          "value range", values.min(), values.max())
 
 
 if __name__ == "__main__":

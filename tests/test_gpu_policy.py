@@ -1,11 +1,13 @@
 """K5 -- the fused policy rollout (tcgen05 MLP + env step in one kernel) on the GPU.
 
-Tolerances.  The three dense layers run with bf16 operands (LayerNorm centring and gamma folded into
-the weight images by dd_policy_pack) and fp32 accumulation, so against the notebook's eager fp32 network the logits differ by up to ~6e-2 (measured 0.063 max on the fixture
-batch by a bf16-operand emulation in torch): probabilities are compared with atol 3e-2, and
-thresholded actions may only differ where the fp32 |logit| < 0.15.  Against the bf16-operand
-emulation (same roundings, different summation order) the kernel must agree to 3e-3 -- that is
-the check that the UMMA descriptors / layouts / LayerNorm epilogues are right.
+Tolerances.  The dense layers run on the tensor cores with bf16 operands (LayerNorm centring and gamma
+folded into the weight images by dd_policy_pack; the first layer in split bf16, ~16 mantissa bits) and fp32
+accumulation, so against the notebook's eager fp32 network the logits differ by up to ~2e-2 (measured 0.020
+max on the fixture batch by an emulation of the same roundings in torch): probabilities are compared with
+atol 1e-2, and thresholded actions may only differ where the fp32 |logit| < 0.05.  Against that emulation
+(same roundings, different summation order) the kernel must agree to 3e-3 -- that is the check that the
+UMMA descriptors / layouts / LayerNorm epilogues are right.  The critic (values of magnitude ~250) is
+compared relative to that scale.
 The environment half is exact: replaying the actions the fused kernel chose through dd_rollout
 must reproduce rewards, flags and final state bit for bit.
 """
@@ -61,20 +63,29 @@ def _ln_folded(xpp, ig, be):
     return xpp * torch.rsqrt(var + 1e-5) + be
 
 
-def _emulate_bf16(sd, x):
-    """Same operand roundings as the kernel: LayerNorm centring and gamma folded into bf16 weight images
-    (b0 rides in the image as one bf16, b1/b2 as bf16 hi + lo), bf16 inputs / hidden activations, fp32
-    accumulation, fp32 variance + normalisation, fp32 last layer."""
+def _split(t):
+    hi = _bf(t)
+    return hi, _bf(t - hi)
+
+
+def _emulate_bf16(sd, x, head=3):
+    """Same operand roundings as the kernel: LayerNorm centring and gamma folded into the weight images;
+    first layer in split bf16 (x_hi W_hi + x_hi W_lo + x_lo W_hi, b0 riding as column 15 against a constant 1);
+    b1/b2 as bf16 hi + lo; bf16 hidden activations and weights, fp32 accumulation, fp32 variance +
+    normalisation, fp32 last layer.  head=3: sigmoid probabilities; head=1: the critic's raw value."""
     W0, b0, ig0 = _fold(sd["network.0.weight"], sd["network.0.bias"], sd["network.1.weight"])
     W1, b1, ig1 = _fold(sd["network.3.weight"], sd["network.3.bias"], sd["network.4.weight"])
     W2, b2, ig2 = _fold(sd["network.6.weight"], sd["network.6.bias"], sd["network.7.weight"])
-    h = _bf(x) @ _bf(W0).T + _bf(b0)
+    x16 = torch.cat([x, torch.ones(x.shape[0], 1)], 1)
+    (xh, xl), (wh, wl) = _split(x16), _split(torch.cat([W0, b0[:, None]], 1))
+    h = xh @ wh.T + xh @ wl.T + xl @ wh.T
     h = torch.relu(_ln_folded(h, ig0, sd["network.1.bias"]))
     h = _bf(h) @ _bf(W1).T + _hi_lo(b1)
     h = torch.relu(_ln_folded(h, ig1, sd["network.4.bias"]))
     h = _bf(h) @ _bf(W2).T + _hi_lo(b2)
     h = torch.relu(_ln_folded(h, ig2, sd["network.7.bias"]))
-    return torch.sigmoid(h @ sd["network.9.weight"].T + sd["network.9.bias"])
+    z = h @ sd["network.9.weight"].T + sd["network.9.bias"]
+    return torch.sigmoid(z) if head == 3 else z.squeeze(-1)
 
 
 def test_forward_matches_torch_on_the_reference_checkpoint(fixture):
@@ -86,9 +97,9 @@ def test_forward_matches_torch_on_the_reference_checkpoint(fixture):
     ref = torch.from_numpy(d["probs"])
     assert torch.isfinite(probs).all()
     assert (probs - emu).abs().max().item() < 3e-3, (probs - emu).abs().max().item()
-    assert (probs - ref).abs().max().item() < 3e-2
+    assert (probs - ref).abs().max().item() < 1e-2, (probs - ref).abs().max().item()
     flips = (probs > 0.5) != (ref > 0.5)
-    assert np.abs(d["logits"])[flips.numpy()].max(initial=0.0) < 0.15
+    assert np.abs(d["logits"])[flips.numpy()].max(initial=0.0) < 0.05
     # the module-based constructor gives the same blob
     blob2 = dd.PolicyBlob.from_module(pol.reference_policy(sd), device=DEV)
     assert torch.equal(blob.blob, blob2.blob)
@@ -241,6 +252,63 @@ def test_rollout_ragged_sizes_use_the_fallback_obs_store(fixture, n):
     obs = torch.empty(T, n, 15, device=DEV); rew = torch.empty(T, n, device=DEV)
     b.rollout(T, "trace", actions=out["actions"], reward_out=rew, obs_out=obs)
     assert torch.equal(out["obs"][0], first) and torch.equal(out["obs"][1:], obs[:-1]) and torch.equal(out["reward"], rew)
+
+
+def test_critic_value_forward_and_rollout_values(fixture, golden_dir):
+    """DroneTeacherBoi (same trunk, Linear(64, 1)) through the same tensor-core path: the reference's critic
+    checkpoint against its eager fp32 values, the persistent forward over a [T, N, 15] rollout buffer (TMA-fed
+    full tiles + ragged tail), and the [T+1, N] values that feed dd_gae."""
+    d, sd = fixture
+    c = np.load(os.path.join(golden_dir, "critic_v1.npz"))
+    sdc = {k_: torch.from_numpy(c[k_]) for k_ in c.files if k_.startswith("network")}
+    vblob = dd.ValueBlob(sdc, device=DEV)
+    x = torch.from_numpy(c["obs"])
+    ref = torch.from_numpy(c["values"])
+    v = dd.value_forward(vblob, x.to(DEV)).cpu()
+    emu = _emulate_bf16(sdc, x, head=1)
+    scale = ref.std().item()
+    assert v.shape == ref.shape and torch.isfinite(v).all()
+    assert ((v - emu).abs() / (1 + emu.abs())).max().item() < 2e-3, ((v - emu).abs() / (1 + emu.abs())).max().item()
+    assert (v - ref).abs().max().item() < 0.02 * scale and (v - ref).pow(2).mean().sqrt().item() < 0.003 * scale
+    # persistent forward over a rollout buffer: same rows -> same values, whatever the launch shape
+    blob = dd.PolicyBlob(sd, device=DEV)
+    n, T = 1000, 37
+    env = dd.BatchedDroneEnv(n, device=DEV, seed=5, randomize_drone=True, randomize_platform=True, max_steps=60,
+                             auto_reset=True, dtype=torch.float32)
+    env.reset()
+    out = dd.policy_rollout(env, blob, T, sample=True, want="rdo")
+    final_obs = env.observe().clone()
+    vals = dd.rollout_values(vblob, out["obs"], final_obs)
+    assert vals.shape == (T + 1, n)
+    for t in (0, 11, T - 1):
+        assert torch.equal(vals[t], dd.value_forward(vblob, out["obs"][t]))
+    assert torch.equal(vals[T], dd.value_forward(vblob, final_obs))
+    flat = dd.value_forward(vblob, out["obs"].view(-1, 15)[3:-5])            # unaligned start, ragged length
+    assert torch.equal(flat, vals[:T].reshape(-1)[3:-5])
+    with torch.no_grad():
+        eager = pol.reference_policy(sdc, head=1)(out["obs"].cpu().view(-1, 15)).squeeze(-1)
+    assert (vals[:T].cpu().reshape(-1) - eager).abs().max().item() < 0.03 * scale
+    # ... and straight into GAE + advantage normalisation (bit-exact against the notebook's loop: test_gpu_parity)
+    adv = dd.normalize_advantages(dd.gae(out["reward"], vals, (out["done"] != 0).to(torch.uint8)), reduce=False)
+    assert adv.shape == (T, n) and torch.isfinite(adv).all()
+    # argument checks
+    with pytest.raises(ValueError):
+        dd.value_forward(blob, x.to(DEV))
+    with pytest.raises(ValueError):
+        dd.policy_forward(vblob, x.to(DEV))
+
+
+def test_policy_forward_large_persistent(fixture):
+    """More row blocks than SMs: the persistent forward (each CTA walks several blocks, next tile prefetched
+    by TMA) must give the same probabilities as block-sized calls."""
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    g = torch.Generator().manual_seed(0)
+    base = torch.from_numpy(d["obs"])
+    x = (base[torch.randint(0, base.shape[0], (200_003,), generator=g)] * (1 + 0.01 * torch.randn(200_003, 15, generator=g))).to(DEV)
+    big = dd.policy_forward(blob, x)
+    for lo in (0, 65_536, 199_000):
+        assert torch.equal(big[lo:lo + 1003], dd.policy_forward(blob, x[lo:lo + 1003].contiguous()))
 
 
 def test_policy_argument_errors(fixture):
