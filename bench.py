@@ -358,6 +358,26 @@ def run_ours(args):
                              "value": NF * TP * reps_p * ws / (ms_full * 1e-3),
                              "mlp_tflops": NF * TP * reps_p / (ms_full * 1e-3) * FLOP_STEP / 1e12}
         del fenv, fbuf
+        # what follows the rollout in the PPO loop (Actor_Critic_PPO.ipynb, PHASE 2): critic values over the stored
+        # states + bootstrap row, compute_gae, advantage normalisation -- all on the rollout buffers in HBM
+        cfix = np.load(os.path.join(ROOT, "tests", "golden", "critic_v1.npz"))
+        vblob = dd.ValueBlob({kk: torch.from_numpy(cfix[kk]) for kk in cfix.files if kk.startswith("network")}, device=dev)
+        final_obs = penv.observe().clone()
+        vals = dd.rollout_values(vblob, pbuf["obs"], final_obs)
+        dones = (pbuf["done"] != 0).to(torch.uint8)
+        adv = dd.gae(pbuf["reward"], vals, dones)
+        nadv = torch.empty_like(adv)
+
+        def run_ppo_tail(kk):
+            for _ in range(kk):
+                dd.rollout_values(vblob, pbuf["obs"], final_obs)
+                dd.gae(pbuf["reward"], vals, dones, out=adv)
+                dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
+        ms_tail = timed(lambda: run_ppo_tail(1), lambda: run_ppo_tail(reps_p))
+        launches += 5 * reps_p
+        k5["ppo_data_path"] = {"what": "critic values [T+1,N] (tcgen05, persistent forward) + GAE + advantage normalisation on the rollout buffers",
+                               "ms": ms_tail / reps_p, "samples_per_s": NP * TP * reps_p * ws / (ms_tail * 1e-3),
+                               "rollout_plus_tail_ms": (ms_pol + ms_tail) / reps_p}
 
     # ---- BASELINE configs[4]: curriculum sweep 75 -> 250, 2M envs per GPU, stats all-reduced over ranks ----
     cur = None

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--want", default="arldo")
     ap.add_argument("--threshold", action="store_true")
+    ap.add_argument("--values", action="store_true", help="also time critic values over the buffer, GAE, normalisation")
     args = ap.parse_args()
     dev = "cuda:0"
     d = np.load(os.path.join(ROOT, "tests", "golden", "policy_v1.npz"))
@@ -43,9 +44,48 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
     steps = args.envs * args.T
-    print(json.dumps({"kernel": "policy_rollout_kernel", "envs": args.envs, "T": args.T, "want": args.want,
-                      "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
-                      "mlp_tflops": steps * 53376 / ms * 1e3 / 1e12, "stats": env.stats()}))
+    out = {"kernel": "policy_rollout_kernel", "envs": args.envs, "T": args.T, "want": args.want,
+           "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
+           "mlp_tflops": steps * 53376 / ms * 1e3 / 1e12, "stats": env.stats()}
+    if args.values and "obs" in buf:
+        # the critic over the whole rollout buffer + bootstrap row, then GAE and advantage normalisation
+        c = np.load(os.path.join(ROOT, "tests", "golden", "critic_v1.npz"))
+        vblob = dd.ValueBlob({k: torch.from_numpy(c[k]) for k in c.files if k.startswith("network")}, device=dev)
+        final_obs = env.observe().clone()
+        vals = dd.rollout_values(vblob, buf["obs"], final_obs)
+        done = (buf["done"] != 0).to(torch.uint8)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        for _ in range(args.reps):
+            vals = dd.rollout_values(vblob, buf["obs"], final_obs)
+        ev[1].record()
+        adv = dd.gae(buf["reward"], vals, done)
+        ev[1].record()
+        for _ in range(args.reps):
+            dd.gae(buf["reward"], vals, done, out=adv)
+        ev[2].record()
+        for _ in range(args.reps):
+            nadv = dd.normalize_advantages(adv, reduce=False)
+        ev[3].record()
+        mom = torch.zeros(3, dtype=torch.float64, device=dev)
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev2[0].record()
+        for _ in range(args.reps):
+            dd.advantage_moments(adv, out=mom)
+        ev2[1].record()
+        for _ in range(args.reps):
+            dd.normalize_advantages(adv, reduce=False, out=nadv)
+        ev2[2].record()
+        torch.cuda.synchronize()
+        out["moments_only_ms"] = ev2[0].elapsed_time(ev2[1]) / args.reps
+        out["normalize_into_out_ms"] = ev2[1].elapsed_time(ev2[2]) / args.reps
+        out["values_ms"] = ev[0].elapsed_time(ev[1]) / args.reps
+        out["values_rows_per_s"] = (steps + args.envs) / out["values_ms"] * 1e3
+        out["values_mlp_tflops"] = (steps + args.envs) * 2 * (15 * 128 + 128 * 128 + 128 * 64 + 64) / out["values_ms"] * 1e3 / 1e12
+        out["gae_ms"] = ev[1].elapsed_time(ev[2]) / args.reps
+        out["normalize_ms"] = ev[2].elapsed_time(ev[3]) / args.reps
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

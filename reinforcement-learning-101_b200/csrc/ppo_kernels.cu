@@ -91,24 +91,43 @@ __global__ void __launch_bounds__(kRedBlock) normalize_kernel(const float* __res
 // fp32 throughout, in the operation order of the torch original (python scalars gamma, gamma*lambda
 // are combined in double and rounded to fp32 when they meet the tensors).  No FMA contraction, so
 // the result is bit-identical to the eager torch loop.
-__global__ void __launch_bounds__(kRedBlock) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
-                                                         const uint8_t* __restrict__ done, float* __restrict__ adv,
-                                                         float* __restrict__ ret, float g, float gl, int32_t T, int64_t n)
+// The scan is a dependent chain only through `gae` (4 dependent fp32 operations per step); the loads are not on
+// it.  A thread-per-env scan has little parallelism at PPO sizes (65,536 envs = 443 threads per SM), so the
+// loop works in chunks of kGaeUnroll steps whose 3 x kGaeUnroll loads are all issued before the first is used:
+// the launch is bound by DRAM latency / kGaeUnroll instead of DRAM latency per step.
+constexpr int kGaeBlock = 64;
+constexpr int kGaeUnroll = 10;
+
+__global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                        const uint8_t* __restrict__ done, float* __restrict__ adv,
+                                                        float* __restrict__ ret, float g, float gl, int32_t T, int64_t n)
 {
-    const int64_t i = (int64_t)blockIdx.x * kRedBlock + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
     if (i >= n) return;
     float gae = 0.0f;
     float v_next = __ldg(val + (int64_t)T * n + i);
-    // software prefetch one step ahead: the scan is a dependent chain only through `gae`
-    for (int32_t t = T - 1; t >= 0; --t) {
-        const int64_t o = (int64_t)t * n + i;
-        const float r = __ldg(rew + o), v = __ldg(val + o);
-        const float mask = done[o] ? 0.0f : 1.0f;
-        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, v_next), mask)), v);
-        gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, mask), gae));
-        adv[o] = gae;
-        if (ret) ret[o] = __fadd_rn(gae, v);
-        v_next = v;
+    for (int32_t t1 = T; t1 > 0; t1 -= kGaeUnroll) {            // steps t1-1 ... max(t1-kGaeUnroll, 0)
+        float r[kGaeUnroll], v[kGaeUnroll];
+        uint8_t d[kGaeUnroll];
+#pragma unroll
+        for (int j = 0; j < kGaeUnroll; ++j) {
+            const int32_t t = t1 - 1 - j;
+            const int64_t o = (int64_t)(t >= 0 ? t : 0) * n + i;
+            r[j] = __ldg(rew + o); v[j] = __ldg(val + o); d[j] = __ldg(done + o);
+        }
+#pragma unroll
+        for (int j = 0; j < kGaeUnroll; ++j) {
+            const int32_t t = t1 - 1 - j;
+            if (t >= 0) {
+                const int64_t o = (int64_t)t * n + i;
+                const float mask = d[j] ? 0.0f : 1.0f;
+                const float delta = __fsub_rn(__fadd_rn(r[j], __fmul_rn(__fmul_rn(g, v_next), mask)), v[j]);
+                gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, mask), gae));
+                adv[o] = gae;
+                if (ret) ret[o] = __fadd_rn(gae, v[j]);
+                v_next = v[j];
+            }
+        }
     }
 }
 
@@ -151,8 +170,8 @@ int dd_gae(const float* rewards_tn, const float* values_t1n, const uint8_t* done
     if (!rewards_tn || !values_t1n || !dones_tn || !adv_tn) return DD_E_NULL;
     if (n < 0 || T < 0) return DD_E_RANGE;
     if (n == 0 || T == 0) return 0;
-    const int grid = (int)((n + dd::kRedBlock - 1) / dd::kRedBlock);
-    dd::gae_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn,
+    const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
+    dd::gae_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn,
                                                                        (float)gamma, (float)(gamma * lambda), T, n);
     return (int)cudaGetLastError();
 }

@@ -27,17 +27,25 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma: float = 0.99,
-        lambda_: float = 0.95, want_returns: bool = False):
+        lambda_: float = 0.95, want_returns: bool = False, out: Optional[torch.Tensor] = None,
+        out_returns: Optional[torch.Tensor] = None):
     """``rewards`` fp32 [T,N], ``values`` fp32 [T+1,N] (bootstrap row last), ``dones`` uint8 [T,N]
-    (non-zero = episode ended on that step).  Returns advantages [T,N] (and returns = adv + V)."""
+    (non-zero = episode ended on that step).  Returns advantages [T,N] (and returns = adv + V).
+    ``out`` / ``out_returns``: preallocated fp32 [T,N] result buffers."""
     _need(rewards, torch.float32, "rewards")
     _need(values, torch.float32, "values")
     _need(dones, torch.uint8, "dones")
     T, n = rewards.shape
     if tuple(values.shape) != (T + 1, n) or tuple(dones.shape) != (T, n):
         raise ValueError("values must be [T+1,N] and dones [T,N]")
-    adv = torch.empty_like(rewards)
-    ret = torch.empty_like(rewards) if want_returns else None
+    for o_, nm in ((out, "out"), (out_returns, "out_returns")):
+        if o_ is not None:
+            _need(o_, torch.float32, nm)
+            if tuple(o_.shape) != (T, n):
+                raise ValueError(f"{nm} must be [T,N]")
+    adv = torch.empty_like(rewards) if out is None else out
+    want_returns = want_returns or out_returns is not None
+    ret = (torch.empty_like(rewards) if out_returns is None else out_returns) if want_returns else None
     nv.check(nv.lib().dd_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), adv.data_ptr(),
                              None if ret is None else ret.data_ptr(), float(gamma), float(lambda_), T, n,
                              _stream(rewards)), "dd_gae")
