@@ -46,7 +46,10 @@
 namespace dd {
 
 constexpr int kTile = 128;                     // envs per tile == UMMA M == TMEM lanes
-constexpr int kGroups = 4;                     // tiles per CTA
+#ifndef DD_K5_GROUPS
+#define DD_K5_GROUPS 4
+#endif
+constexpr int kGroups = DD_K5_GROUPS;          // tiles per CTA (4 = all 512 TMEM columns; fewer only for experiments)
 constexpr int kPolThreads = kTile * kGroups;   // 512
 constexpr int kH1 = 128, kH2 = 128, kH3 = 64, kIn = 15, kInPad = 16, kOut = 3;
 
