@@ -408,13 +408,13 @@ def run_ours(args):
         for j in range(k):
             b = io[j % len(io)]
             b["actions"].copy_(host_trace[j % TRACE])     # host-side: the caller's actions of this step
-            envs[j % S].step_host(b)
+            envs[j % S].step_host(b, chunks=args.e2e_chunks)
     t0 = None
 
     def run_e2e_timed():
         run_e2e(Ke)
     ms_e2e = timed(lambda: run_e2e(3), run_e2e_timed)
-    launches += Ke
+    launches += Ke * max(1, args.e2e_chunks)
     h2d = n * 1
     d2h = n * (envs[0].obs_stride * 4 + 4 + 1)
 
@@ -453,7 +453,9 @@ def run_ours(args):
             },
             "e2e": {"value": n * Ke * ws / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e2e / Ke,
-                    "api": "BatchedDroneEnv.step_host (pinned host actions in; obs, reward, flags out)"},
+                    "api": f"BatchedDroneEnv.step_host(chunks={args.e2e_chunks}) (pinned host actions in; obs, reward, flags out)",
+                    "pcie_gbs": (h2d + d2h) / (ms_e2e / Ke * 1e-3) / 1e9,
+                    "bound": "PCIe: 65 B per env-step device->host (obs 60 + reward 4 + flags 1)"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "episode_stats_shard0": stats,
@@ -485,6 +487,7 @@ def main():
     ap.add_argument("--shards", type=int, default=6, help="independent shards per GPU that steps rotate over")
     ap.add_argument("--chains", type=int, default=2, help="parallel launch chains in the CUDA graph (shard s -> chain s %% chains)")
     ap.add_argument("--e2e-steps", type=int, default=300)
+    ap.add_argument("--e2e-chunks", type=int, default=1, help="step_host pipelines the step over this many env slices (D2H of slice k overlaps H2D + kernel of slice k+1)")
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy", action="store_true", help="skip the fused policy rollout variant (K5)")
