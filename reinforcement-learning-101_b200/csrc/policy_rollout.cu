@@ -137,6 +137,16 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "n"(kTile) : "memory"); }
+// Wait for the tile's committed MMAs.  Only the issuing warp polls the mbarrier (try_wait returns after a short
+// system-defined time, so a waiting warp keeps executing a poll loop that competes for issue slots: ~200
+// instructions per thread-step when all four warps of a tile poll); the other three block on a second named
+// barrier that the issuing warp joins once the phase has flipped.
+__device__ __forceinline__ void wait_mma(uint32_t bar, uint32_t& phase, bool issuer_warp, int g) {
+    if (issuer_warp) mbar_wait(bar, phase);
+    phase ^= 1u;
+    asm volatile("bar.sync %0, %1;" :: "r"(g + 1 + kGroups), "n"(kTile) : "memory");
+    tc_fence_after();
+}
 
 // UMMA shared-memory matrix descriptor: K-major, no swizzle, 8x16-byte core matrices.
 //   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (next 16-byte K chunk)
@@ -460,7 +470,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                                 (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             pin(rnd.a); pin(rnd.b); pin(rnd.c);
         }
-        mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
+        wait_mma(bar, phase, issuer_warp, g);
         ln_epilogue<kH1, CH>(trow, pc.inv_gamma0, pc.beta0,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
@@ -475,7 +485,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w1b_addr, kH2 * 16, 128), umma_idesc(128, kH2), 1u);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
+        wait_mma(bar, phase, issuer_warp, g);
         ln_epilogue<kH2, CH>(trow, pc.inv_gamma1, pc.beta1,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
@@ -489,7 +499,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3), 1u);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase); phase ^= 1u; __syncwarp(); tc_fence_after();
+        wait_mma(bar, phase, issuer_warp, g);
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
         ln_epilogue<kH3, CH>(trow, pc.inv_gamma2, pc.beta2, [&](int c, const float (&y)[CH]) {
