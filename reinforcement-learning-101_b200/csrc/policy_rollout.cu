@@ -305,7 +305,8 @@ __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int
 // observations (parity hook for the policy; the critic's values over a rollout buffer), persistent over blocks of
 // 512 rows: the "step" loop walks row blocks and the observation tile of the NEXT block is fetched by TMA
 // (cp.async.bulk -> mbarrier) while the current one goes through the layers.
-template <bool DEF, int CH, bool FWD>
+// HEAD: 3 = policy (probabilities); 1 = critic (FWD only): the two unused rows of the last Linear are not computed.
+template <bool DEF, int CH, bool FWD, int HEAD = 3>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -509,14 +510,16 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                 const float2 h1 = make_float2(fmaxf(y[4 * j + 2], 0.f), fmaxf(y[4 * j + 3], 0.f));
                 const int col = c * CH + 4 * j;
                 za = __ffma2_rn(h0, make_float2(pc.w3[0][col], pc.w3[0][col + 1]), za); za = __ffma2_rn(h1, make_float2(pc.w3[0][col + 2], pc.w3[0][col + 3]), za);
-                zb = __ffma2_rn(h0, make_float2(pc.w3[1][col], pc.w3[1][col + 1]), zb); zb = __ffma2_rn(h1, make_float2(pc.w3[1][col + 2], pc.w3[1][col + 3]), zb);
-                zc = __ffma2_rn(h0, make_float2(pc.w3[2][col], pc.w3[2][col + 1]), zc); zc = __ffma2_rn(h1, make_float2(pc.w3[2][col + 2], pc.w3[2][col + 3]), zc);
+                if (HEAD == 3) {
+                    zb = __ffma2_rn(h0, make_float2(pc.w3[1][col], pc.w3[1][col + 1]), zb); zb = __ffma2_rn(h1, make_float2(pc.w3[1][col + 2], pc.w3[1][col + 3]), zb);
+                    zc = __ffma2_rn(h0, make_float2(pc.w3[2][col], pc.w3[2][col + 1]), zc); zc = __ffma2_rn(h1, make_float2(pc.w3[2][col + 2], pc.w3[2][col + 3]), zc);
+                }
             }
         });
         const float z0 = za.x + za.y + pc.b3[0], z1 = zb.x + zb.y + pc.b3[1], z2 = zc.x + zc.y + pc.b3[2];
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         const float p0 = 1.0f / (1.0f + __expf(-z0)), p1 = 1.0f / (1.0f + __expf(-z1)), p2 = 1.0f / (1.0f + __expf(-z2));
-        if (FWD && pa.head == 1) {                           // critic: the raw scalar (DroneTeacherBoi, c12)
+        if (FWD && HEAD == 1) {                           // critic: the raw scalar (DroneTeacherBoi, c12)
             if (live) pa.probs_tn[o] = z0;
         } else if (out_probs && live) {
             float* dst = pa.probs_tn + o * kOut;
@@ -682,7 +685,7 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
     void (*kern)(PArgs);
     int grid = blocks;
     if (forward) {
-        kern = policy_rollout_kernel<true, kChunk, true>;
+        kern = pa.head == 1 ? policy_rollout_kernel<true, kChunk, true, 1> : policy_rollout_kernel<true, kChunk, true, 3>;
         int dev = 0, sms = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
