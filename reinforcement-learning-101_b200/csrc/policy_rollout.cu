@@ -20,23 +20,29 @@
 //     bf16 hi + lo), so the accumulator row is  x''_j = gamma_j (x_j - mean(x)).  What is left for the
 //     CUDA cores is  var = 1/N sum_j (x''_j / gamma_j)^2  (pass 1: FMUL2 + FFMA2 per column pair) and
 //     y_j = x''_j * rstd + beta_j  (pass 2: one FFMA2, ReLU inside the bf16 conversion), i.e. 4
-//     instructions per pair instead of 7 and a third of the shared-memory parameter traffic;
+//     instructions per pair instead of 7;
+//   * 1/gamma, beta and the last Linear travel by value in the kernel argument (DDPolicyConsts): after
+//     unrolling every access is c[0][imm] -> LDCU.128 -> a uniform-register operand of FFMA2 / FMUL2, no
+//     shared-memory loads in the epilogues;
 //   * the first layer runs in split-bf16 precision: observation and layer-0 image are hi + lo bf16 pairs and
 //     D = x_hi W_hi + x_hi W_lo + x_lo W_hi (three K = 16 MMAs instead of one, ~16 mantissa bits): the input
 //     rounding was 3/4 of the whole network's bf16 error (positions quantised to 1/512) -- measured on the
 //     reference checkpoints: max logit error 0.090 -> 0.020, critic value error 8.9 -> 2.4 (std 254);
-//   * each thread reads its accumulator row with `tcgen05.ld.32x32b.x32` (SASS LDTM), twice,
+//   * each thread reads its accumulator row with `tcgen05.ld.32x32b.x16` (SASS LDTM), twice,
 //     double-buffered (chunk c+1 is in flight while chunk c is processed) and writes the next A tile
 //     straight into the UMMA layout;
-//   * weights (bf16, already in UMMA layout) + LN parameters live in shared memory for the whole
-//     kernel (61 KB) + the ones block (4 KB), the A tiles take 32 KB per tile: 194 KB of the 227 KB;
+//   * the operand images (bf16, already in UMMA layout; 62 KB) + the ones block (4 KB) live in shared
+//     memory for the whole kernel, the A tiles take 32 KB per tile, the observation staging tiles
+//     (one TMA bulk store per tile-step) 7.5 KB per tile: 224 KB of the 227 KB;
 //   * the last layer (64 -> 3) and the sigmoid / Bernoulli / log-prob are folded into the third
 //     epilogue on the CUDA cores; the environment step is `step_core` from drone_core.cuh, the
 //     same code as K1, so the environment side is bit-identical to dd_rollout on the same actions.
 // The four tiles of a CTA are independent pipelines, so while one waits for its MMAs the other three
-// keep the CUDA cores busy; work that does not depend on the network output (Philox draws, the
-// observation stores) is placed under the first MMA.  The kernel is bound by the epilogue arithmetic
-// and its latencies (4 warps per scheduler), not by the tensor pipe (profiles/README.md).
+// keep the CUDA cores busy; work that does not depend on the network output (Philox draws, sin / cos of
+// the pre-update angle, the observation store) is placed under the first MMA.  Measured:
+// T(k tiles per SM) = 0.70 ms + k x 0.21 ms per 250 steps -- the slope is the issue slots of one more warp
+// per scheduler (~1,770 instructions per env-step), the intercept the latency of one tile's serial chain;
+// the tensor pipe is ~40 % busy.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -70,11 +76,11 @@ constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 66,832
 static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
 static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
 static_assert(sizeof(DDPolicyConsts) == kParFloats * 4, "the blob's fp32 section is a DDPolicyConsts image");
-constexpr float kGammaFloor = 1e-12f;
+constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this is treated as +-1e-12
 #ifndef DD_K5_CHUNK
 #define DD_K5_CHUNK 16
 #endif
-constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (16 or 32)                      // |gamma| below this is treated as +-1e-12
+constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (8, 16 or 32; 16 measured best)
 
 constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
 constexpr int kSmemBlob = 0;
