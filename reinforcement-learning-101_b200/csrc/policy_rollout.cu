@@ -38,8 +38,10 @@
 //     epilogue on the CUDA cores; the environment step is `step_core` from drone_core.cuh, the
 //     same code as K1, so the environment side is bit-identical to dd_rollout on the same actions.
 // The four tiles of a CTA are independent pipelines, so while one waits for its MMAs the other three
-// keep the CUDA cores busy; work that does not depend on the network output (Philox draws, sin / cos of
-// the pre-update angle, the observation store) is placed under the first MMA.  Measured:
+// keep the CUDA cores busy; work that is not on the chain obs -> network -> action -> env step -> obs runs in
+// the shadow of an MMA, where the warp would otherwise sleep: the previous step's log-prob / output stores /
+// statistics under the first, the Philox draws under the second, sin / cos of the pre-update angle under the
+// third.  Measured:
 // T(k tiles per SM) = 0.70 ms + k x 0.21 ms per 250 steps -- the slope is the issue slots of one more warp
 // per scheduler (~1,770 instructions per env-step), the intercept the latency of one tile's serial chain;
 // the tensor pipe is ~40 % busy.
@@ -410,6 +412,27 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     float dprev = nan_of<float>(), dcur = dist * k.inv_width;
     if (live && shaping) dprev = a.prev_dist[i];
 
+    // Outputs of a step that nothing in the NEXT step's network input depends on (log-prob, the action / log-prob /
+    // reward / done / shaped stores, the statistics commit) are deferred: they run under the first MMA of the next
+    // step, where the warp would otherwise sleep, instead of in front of it on the tile's serial chain.
+    struct Pending { float p0, p1, p2, reward, shaped, ret_stat; uint32_t act, oflags, f_stat; int32_t len_stat; } pend = {};
+    auto flush_pending = [&](size_t o_prev) {
+        if (live) {
+            if (shaping) pa.shaped_tn[o_prev] = pend.shaped;
+            if (out_act) pa.actions_tn[o_prev] = (uint8_t)pend.act;
+            if (out_logp) {                                  // Bernoulli(probs).log_prob(a).sum(), probs clamped like torch
+                const float eps = 1.1920929e-07f;
+                const float q0 = fminf(fmaxf(pend.p0, eps), 1.f - eps), q1 = fminf(fmaxf(pend.p1, eps), 1.f - eps),
+                            q2 = fminf(fmaxf(pend.p2, eps), 1.f - eps);
+                pa.logp_tn[o_prev] = __logf((pend.act & DD_ACT_MAIN) ? q0 : 1.f - q0) + __logf((pend.act & DD_ACT_LEFT) ? q1 : 1.f - q1) +
+                                     __logf((pend.act & DD_ACT_RIGHT) ? q2 : 1.f - q2);
+            }
+            if (out_rew) pa.reward_tn[o_prev] = pend.reward;
+            if (out_done) pa.done_tn[o_prev] = (uint8_t)pend.oflags;
+        }
+        if (do_stats) stats_warp_commit(a.stats, pend.f_stat, pend.ret_stat, pend.len_stat);
+    };
+
     for (int32_t t = 0; t < pa.T; ++t) {
         const size_t o = FWD ? (size_t)i : (size_t)t * a.n + i;
         // ---------------- observation -> A0 (bf16, K = 16: 15 inputs + constant 1 for the bias) -------
@@ -469,14 +492,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
         }
-        float s_pre = 0.f, c_pre = 1.f;                      // sin / cos of the pre-update angle (main thrust, drone.py:58-66)
-        if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }
-        U4 rnd = {0u, 0u, 0u, 0u};
-        if (!forward_only && !thresholded) {
-            rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
-                                (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-            pin(rnd.a); pin(rnd.b); pin(rnd.c);
-        }
+        if (!forward_only && t > 0) flush_pending(o - a.n);
         wait_mma(bar, phase, issuer_warp, g);
         ln_epilogue<kH1, CH>(trow, pc.inv_gamma0, pc.beta0,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
@@ -492,6 +508,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w1b_addr, kH2 * 16, 128), umma_idesc(128, kH2), 1u);
             umma_commit(bar);
         }
+        U4 rnd = {0u, 0u, 0u, 0u};                           // under the second MMA: this step's Philox draws
+        if (!forward_only && !thresholded) {
+            rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
+                                (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            pin(rnd.a); pin(rnd.b); pin(rnd.c);
+        }
         wait_mma(bar, phase, issuer_warp, g);
         ln_epilogue<kH2, CH>(trow, pc.inv_gamma1, pc.beta1,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
@@ -506,6 +528,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3), 1u);
             umma_commit(bar);
         }
+        float s_pre = 0.f, c_pre = 1.f;                      // under the third MMA: sin / cos of the pre-update angle
+        if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }   // (main thrust, drone.py:58-66)
         wait_mma(bar, phase, issuer_warp, g);
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
@@ -540,7 +564,6 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 
         // ---------------- action: threshold (c18:L24-25) or Bernoulli sample (c16:L61-63) --------------
         uint32_t act;
-        float logp = 0.f;
         if (thresholded) {
             act = (p0 > 0.5f ? DD_ACT_MAIN : 0u) | (p1 > 0.5f ? DD_ACT_LEFT : 0u) | (p2 > 0.5f ? DD_ACT_RIGHT : 0u);
         } else {
@@ -548,48 +571,37 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                         u2 = (float)(rnd.c >> 8) * (1.0f / 16777216.0f);
             act = (u0 < p0 ? DD_ACT_MAIN : 0u) | (u1 < p1 ? DD_ACT_LEFT : 0u) | (u2 < p2 ? DD_ACT_RIGHT : 0u);
         }
-        if (out_logp) {                                      // Bernoulli(probs).log_prob(a).sum(), probs clamped like torch
-            const float eps = 1.1920929e-07f;
-            const float q0 = fminf(fmaxf(p0, eps), 1.f - eps), q1 = fminf(fmaxf(p1, eps), 1.f - eps), q2 = fminf(fmaxf(p2, eps), 1.f - eps);
-            logp = __logf((act & DD_ACT_MAIN) ? q0 : 1.f - q0) + __logf((act & DD_ACT_LEFT) ? q1 : 1.f - q1) +
-                   __logf((act & DD_ACT_RIGHT) ? q2 : 1.f - q2);
-        }
 
         // ---------------- environment step (same code as K1) -------------------------------------------
         uint32_t oflags = pflags, f_stat = 0;
         float ret_stat = 0; int32_t len_stat = 0;
         float reward = 0.f, shaped = 0.f;
-        if (live) {
-            if (!(pflags & DD_DONE)) {
-                uint32_t f = step_core<float, true, true>(e, act, k, reward, speed, dist, s_pre, c_pre);
-                if (!f && max_steps > 0 && e.steps >= max_steps) f = DD_DONE | DD_TRUNCATED;
-                oflags = f;
-                if (shaping) {
-                    shaped = shaped_reward_ppo(e, f, speed, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
-                    dprev = dcur;
-                    dcur = Arith<float>::div(dist, k.width, k.inv_width);
-                }
-                if (f) {
-                    f_stat = f; ret_stat = e.ret; len_stat = e.steps;
-                    if (auto_reset) {
-                        spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
-                        ep += 1;
-                        platform_dirty = true;
-                        f = 0;
-                        speed_dist(e, speed, dist);
-                        if (shaping) { dprev = nan_of<float>(); dcur = Arith<float>::div(dist, k.width, k.inv_width); }
-                    }
-                }
-                pflags = f;
+        if (live && !(pflags & DD_DONE)) {
+            uint32_t f = step_core<float, true, true>(e, act, k, reward, speed, dist, s_pre, c_pre);
+            if (!f && max_steps > 0 && e.steps >= max_steps) f = DD_DONE | DD_TRUNCATED;
+            oflags = f;
+            if (shaping) {
+                shaped = shaped_reward_ppo(e, f, speed, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
+                dprev = dcur;
+                dcur = Arith<float>::div(dist, k.width, k.inv_width);
             }
-            if (shaping) pa.shaped_tn[o] = shaped;
-            if (out_act) pa.actions_tn[o] = (uint8_t)act;
-            if (out_logp) pa.logp_tn[o] = logp;
-            if (out_rew) pa.reward_tn[o] = reward;
-            if (out_done) pa.done_tn[o] = (uint8_t)oflags;
+            if (f) {
+                f_stat = f; ret_stat = e.ret; len_stat = e.steps;
+                if (auto_reset) {
+                    spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
+                    ep += 1;
+                    platform_dirty = true;
+                    f = 0;
+                    speed_dist(e, speed, dist);
+                    if (shaping) { dprev = nan_of<float>(); dcur = Arith<float>::div(dist, k.width, k.inv_width); }
+                }
+            }
+            pflags = f;
         }
-        if (do_stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
+        pend.p0 = p0; pend.p1 = p1; pend.p2 = p2; pend.act = act; pend.reward = reward; pend.shaped = shaped;
+        pend.oflags = oflags; pend.f_stat = f_stat; pend.ret_stat = ret_stat; pend.len_stat = len_stat;
     }
+    if (!forward_only && pa.T > 0) flush_pending((size_t)(pa.T - 1) * a.n + i);
 
     if (live && !forward_only) {
         store4(a.pos_vel, i, e.x, e.y, e.vx, e.vy);
