@@ -449,10 +449,6 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             }
         } else {
             write_obs(e, pflags, speed, dist, k, [&](int j, float v) { ob[j] = v; });
-            if (obs_bulk) {
-#pragma unroll
-                for (int j = 0; j < kIn; ++j) s_obs[row * kIn + j] = ob[j];
-            }
         }
         ob[15] = 1.0f;
         // split bf16: hi = bf16(x), lo = bf16(x - hi); K chunks 0-1 = hi, 2-3 = lo
@@ -480,13 +476,13 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                 const uint32_t next0 = tile0 + gridDim.x * (kGroups * kTile);
                 if (t + 1 < pa.T && tile_bulk_in(next0)) fetch_tile(next0);
             }
-            if (obs_bulk) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(pa.obs_tn + ((size_t)t * a.n + tile0) * kIn), "r"(smem_u32(s_obs)), "n"(kObsTileBytes) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
         }
-        // work that does not depend on the network output runs under the first MMA
+        // under the first MMA: the observation leaves (staged for the TMA store issued after the next barrier, or
+        // directly for ragged / unaligned tiles), and the previous step's deferred outputs
+        if (obs_bulk) {
+#pragma unroll
+            for (int j = 0; j < kIn; ++j) s_obs[row * kIn + j] = ob[j];
+        }
         if (obs_out && !obs_bulk && live) {
             float* dst = pa.obs_tn + o * kIn;
 #pragma unroll
@@ -497,10 +493,14 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         ln_epilogue<kH1, CH>(trow, pc.inv_gamma0, pc.beta0,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
-        if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (issuer_warp && elect_one()) {
             tc_fence_after();
+            if (obs_bulk) {                                  // the staged observation tile is complete: one TMA store
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(pa.obs_tn + ((size_t)t * a.n + tile0) * kIn), "r"(smem_u32(s_obs)), "n"(kObsTileBytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
 #pragma unroll
             for (int j = 0; j < kH1 / 16; ++j)
                 umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         ln_epilogue<kH2, CH>(trow, pc.inv_gamma1, pc.beta1,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
+        if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (issuer_warp && elect_one()) {
             tc_fence_after();
