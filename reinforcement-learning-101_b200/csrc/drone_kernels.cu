@@ -166,7 +166,10 @@ struct RArgs {
     int32_t T, policy, auto_reset;
 };
 
-template <typename R, bool OBS, bool DEF>
+// POLICY (the action source) is a template parameter and every launch-constant switch is read once before the
+// loop: the kernel is bound by issue slots (no memory traffic to hide behind), so each instruction of the
+// per-step path is throughput.
+template <typename R, bool OBS, bool DEF, int POLICY>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ RArgs<R> ra)
 {
     __shared__ __align__(128) R s_obs[OBS ? kBlock * kMaxObsStride : 1];
@@ -189,8 +192,19 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     }
     pdl_launch_dependents();
     const uint64_t gid = a.env_id_base + (uint64_t)i;
-    U4 blk = {0, 0, 0, 0};
-    uint32_t blk_id = 0xffffffffu;
+    // DD_POLICY_RANDOM: the 96 action bits of the current block of 32 steps (action_block) as a shift register --
+    // the step's action is its low 3 bits (== action_from_block), then it moves on by 3 bits
+    uint32_t rb0 = 0, rb1 = 0, rb2 = 0, tt = ra.t0;
+    if (POLICY == DD_POLICY_RANDOM) {
+        const U4 b = action_block(a.seed, gid, tt);
+        rb0 = b.a; rb1 = b.b; rb2 = b.c;
+        for (uint32_t j = 0; j < (tt & 31u); ++j) {          // a rollout may start inside a block
+            rb0 = __funnelshift_r(rb0, rb1, 3); rb1 = __funnelshift_r(rb1, rb2, 3); rb2 >>= 3;
+        }
+    }
+    const bool out_rew = ra.reward_tn != nullptr, out_done = ra.done_tn != nullptr, do_stats = a.stats != nullptr,
+               auto_reset = ra.auto_reset != 0;
+    const int32_t max_steps = a.max_steps;
     // N2 (shaped training reward): normalised distance of the current state and of the one before it
     const bool shaping = ra.shaped_tn != nullptr;
     R dprev = nan_of<R>(), dcur = (R)0;
@@ -208,28 +222,32 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
         if (live) {
             const size_t o = (size_t)t * a.n + i;
             uint32_t act;
-            if (ra.policy == DD_POLICY_TRACE) {
+            if (POLICY == DD_POLICY_TRACE) {
                 act = ra.actions_tn[o];
-            } else if (ra.policy == DD_POLICY_RANDOM) {
-                const uint32_t tt = ra.t0 + (uint32_t)t;
-                if ((tt >> 5) != blk_id) { blk = action_block(a.seed, gid, tt); blk_id = tt >> 5; }
-                act = action_from_block(blk, tt);
+            } else if (POLICY == DD_POLICY_RANDOM) {
+                if ((tt & 31u) == 0u && t > 0) {
+                    const U4 b = action_block(a.seed, gid, tt);
+                    rb0 = b.a; rb1 = b.b; rb2 = b.c;
+                }
+                act = rb0 & 7u;
+                rb0 = __funnelshift_r(rb0, rb1, 3); rb1 = __funnelshift_r(rb1, rb2, 3); rb2 >>= 3;
+                ++tt;
             } else {
                 act = (e.vy > (R)1.5) ? DD_ACT_MAIN : 0u;
             }
             if (!(act & DD_ACT_SKIP) && !(pflags & DD_DONE)) {
                 uint32_t f = step_core<R, OBS>(e, act, k, reward, speed, dist);
-                if (!f && a.max_steps > 0 && e.steps >= a.max_steps) f = DD_DONE | DD_TRUNCATED;
+                if (!f && max_steps > 0 && e.steps >= max_steps) f = DD_DONE | DD_TRUNCATED;
                 oflags = f;
                 if (shaping) {
                     const R sp = OBS ? speed : Arith<R>::sqrt_(Arith<R>::fma_(e.vx, e.vx, Arith<R>::mul(e.vy, e.vy)));
-                    shaped = shaped_reward_ppo(e, f, sp, dist, dprev, a.max_steps > 0 && e.steps >= a.max_steps, k);
+                    shaped = shaped_reward_ppo(e, f, sp, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
                     dprev = dcur;
                     dcur = Arith<R>::div(dist, k.width, k.inv_width);
                 }
                 if (f) {
                     f_stat = f; ret_stat = e.ret; len_stat = e.steps;
-                    if (ra.auto_reset) {
+                    if (auto_reset) {
                         spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
                         ep += 1;
                         platform_dirty = true;
@@ -243,15 +261,15 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                 speed_dist(e, speed, dist);
             }
             if (shaping) ra.shaped_tn[o] = shaped;
-            if (ra.reward_tn) ra.reward_tn[o] = reward;
-            if (ra.done_tn) ra.done_tn[o] = (uint8_t)oflags;
+            if (out_rew) ra.reward_tn[o] = reward;
+            if (out_done) ra.done_tn[o] = (uint8_t)oflags;
             if (OBS) {
                 R* row = s_obs + threadIdx.x * a.obs_stride;
                 write_obs(e, pflags, speed, dist, k, [&](int j, R v) { row[j] = v; });
                 if (a.obs_stride > DD_OBS_DIM) row[DD_OBS_DIM] = (R)e.steps;
             }
         }
-        if (a.stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
+        if (do_stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
         if (OBS) {
             obs_tile_store<R, kBlock>(s_obs, ra.obs_tn + ((size_t)t * a.n + tile0) * a.obs_stride, rows, a.obs_stride);
             __syncthreads();                                   // tile is reused next step
@@ -432,12 +450,13 @@ static int rollout_impl(const DDState* s, const DDParams* p, const DDEnvConfig* 
     if (n == 0 || T == 0) return 0;
     const bool pdl = (c->launch_flags & DD_LAUNCH_PDL) != 0, def = params_are_default(*p);
     const int g = grid_for(n, kBlock);
-    if (def) {
-        if (obs_tn) return launch(rollout_kernel<R, true, true>, g, kBlock, st, pdl, ra);
-        return launch(rollout_kernel<R, false, true>, g, kBlock, st, pdl, ra);
-    }
-    if (obs_tn) return launch(rollout_kernel<R, true, false>, g, kBlock, st, pdl, ra);
-    return launch(rollout_kernel<R, false, false>, g, kBlock, st, pdl, ra);
+#define DD_ROLL(OBS_, DEF_)                                                                                        \
+    (policy == DD_POLICY_TRACE    ? launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_TRACE>, g, kBlock, st, pdl, ra)    \
+     : policy == DD_POLICY_RANDOM ? launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_RANDOM>, g, kBlock, st, pdl, ra)   \
+                                  : launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_BANGBANG>, g, kBlock, st, pdl, ra))
+    if (def) return obs_tn ? DD_ROLL(true, true) : DD_ROLL(false, true);
+    return obs_tn ? DD_ROLL(true, false) : DD_ROLL(false, false);
+#undef DD_ROLL
 }
 
 }  // namespace dd
