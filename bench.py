@@ -196,6 +196,42 @@ def _ncu_traffic(n: int):
         return None, "no ncu capture committed"
 
 
+def socket_shim_rate(dev, games: int = 6, seconds: float = 2.0):
+    """Context number: the reference's TCP/JSON protocol served from the batched env -- 6 games,
+    one client stepping them round-robin with random actions, reset on done, like the notebooks do.  The
+    reference documents 300-500 steps/s for its own server (SOCKET_API.md:373); measured 58.5 steps/s at its
+    default --fps 60 and ~6.7e3 with the fps cap lifted."""
+    import random
+    compat = importlib.import_module("reinforcement-learning-101_b200.compat")
+    pool = compat.DroneGamePool(games, device=dev, seed=0, randomize_drone=True, randomize_platform=True)
+    srv = compat.DroneSocketServer(pool, host="127.0.0.1", port=0)
+    srv.start(background=True)
+    cli = compat.DroneGameClient(host="127.0.0.1", port=srv.port, timeout=10.0)
+    rng = random.Random(0)
+    lat = []
+    try:
+        for g in range(games):
+            cli.reset(g)
+        t_end = time.perf_counter() + seconds
+        n = 0
+        while time.perf_counter() < t_end:
+            g = n % games
+            t0 = time.perf_counter()
+            _, _, done, _ = cli.step({"main_thrust": rng.getrandbits(1), "left_thrust": rng.getrandbits(1),
+                                      "right_thrust": rng.getrandbits(1)}, g)
+            lat.append(time.perf_counter() - t0)
+            if done:
+                cli.reset(g)
+            n += 1
+    finally:
+        cli.close()
+        srv.stop()
+    lat.sort()
+    return {"steps_per_s": len(lat) / sum(lat), "median_step_latency_ms": lat[len(lat) // 2] * 1e3,
+            "p99_step_latency_ms": lat[int(len(lat) * 0.99)] * 1e3, "games": games, "steps": len(lat),
+            "what": "compat.DroneSocketServer + DroneGameClient over 127.0.0.1 (the reference's wire protocol), one request per step"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -460,6 +496,11 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "episode_stats_shard0": stats,
         }
+        if ws == 1 and not args.no_socket:
+            try:
+                line["socket_shim"] = socket_shim_rate(dev)
+            except Exception as exc:                       # context only: never fail the bench line over it
+                line["socket_shim"] = {"error": repr(exc)}
         if ws == 1 and not args.no_cpu_baseline:
             ticks = args.cpu_ticks
             agg, per_proc, procs, secs = cpu_port_multiprocess(ticks, 200)
@@ -490,6 +531,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=1, help="step_host pipelines the step over this many env slices (D2H of slice k overlaps H2D + kernel of slice k+1)")
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-socket", action="store_true", help="skip the socket-shim context measurement")
     ap.add_argument("--no-policy", action="store_true", help="skip the fused policy rollout variant (K5)")
     ap.add_argument("--no-curriculum", action="store_true", help="skip the curriculum sweep variant (cfg 5)")
     ap.add_argument("--curriculum-envs", type=int, default=1 << 21, help="envs per GPU in the curriculum sweep")

@@ -177,6 +177,16 @@ int dd_pack_actions(const uint8_t *actions3, uint8_t *packed, int64_t n, void *s
 int dd_stats_collapse(const uint64_t *stats, const int32_t *steps, const uint8_t *flags, int64_t n,
                       uint64_t *out, void *stream);
 
+/* Everything the per-game surfaces (DroneGame.get_state / _get_info / .done .steps .episode, game_engine.py:140-177,
+ * 281-298) read about env i, gathered into ONE record of DD_ENV_RECORD_DOUBLES doubles so that a per-game step of the
+ * socket API costs one small copy instead of ten:  [0..15] obs row of env i (obs_stride 15: [15] = steps),
+ * [16] reward and [17] flags of the last dd_step, [18] persistent flags, [19] steps, [20] episode,
+ * [21..24] pos_vel, [25..28] att_fuel, [29..30] platform, [31] 0.   `out` may be device memory or pinned
+ * (device-mapped) host memory; obs / reward / step_flags may be NULL (zeros). */
+#define DD_ENV_RECORD_DOUBLES 32
+int dd_gather_env(const DDState *s, const void *obs, int32_t obs_stride, const void *reward,
+                  const uint8_t *step_flags, int64_t i, int64_t n, double *out, void *stream);
+
 /* n, sum x, sum x^2 of a float vector into out[3] (device doubles); ACCUMULATES into out.
  * (advantage normalisation moments, Actor_Critic_PPO.ipynb c21:L105) */
 int dd_moments(const float *x, int64_t n, double *out, void *stream);

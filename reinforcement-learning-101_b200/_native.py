@@ -30,6 +30,7 @@ F32, F64 = 0, 1
 POLICY_TRACE, POLICY_RANDOM, POLICY_BANGBANG = 0, 1, 2
 OBS_DIM = 15
 STATS_SLOTS, STATS_WORDS = 64, 8
+ENV_RECORD_DOUBLES = 32
 RETURN_FIXED_SCALE = 1048576.0
 LAUNCH_PDL, LAUNCH_BLOCK_128, LAUNCH_BLOCK_512 = 0x01, 0x10, 0x20
 
@@ -152,6 +153,8 @@ def lib():
     L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
     L.dd_policy_forward.restype = C.c_int
     L.dd_policy_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
+    L.dd_gather_env.restype = C.c_int
+    L.dd_gather_env.argtypes = [PS, vp, i32, vp, vp, i64, i64, vp, vp]
     L.dd_value_pack.restype = C.c_int
     L.dd_value_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
     L.dd_value_forward.restype = C.c_int
@@ -179,5 +182,5 @@ def default_params() -> DDParams:
 EXPORTS = (
     "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout", "dd_rollout_shaped",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
-    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward",
+    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env",
 )

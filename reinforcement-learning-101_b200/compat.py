@@ -19,6 +19,7 @@ batched callers use ``BatchedDroneEnv.step`` directly.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import socket
 import sys
@@ -97,14 +98,20 @@ class DroneGamePool:
                                    obs_stride=16)
         n = num_games
         self.num_games = n
-        self._skip = torch.full((n,), nv.ACT_SKIP, dtype=torch.uint8, device=self.env.device)
-        self._mask = torch.zeros(n, dtype=torch.uint8, device=self.env.device)
+        # Pinned host buffers are device-mapped (unified addressing): the kernels read the per-call action / mask
+        # bytes and write the per-game record straight through them, so one per-game step is two launches and one
+        # stream synchronisation -- no separate copies, no index kernels.
+        self._h_act = torch.full((n,), nv.ACT_SKIP, dtype=torch.uint8).pin_memory()
+        self._h_mask = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._h_rec = torch.zeros(n, nv.ENV_RECORD_DOUBLES, dtype=torch.float64).pin_memory()
+        self._rec_ok = [False] * n                     # record i is current (invalidated when game i changes)
         self._lock = threading.Lock()
         # DroneGame.__init__ (game_engine.py:40-53): fixed start positions, episode = 0, no reset() yet
         p, dev = self.env.params, self.env.device
         full = lambda v: torch.full((n,), float(v), dtype=dtype, device=dev)
         self.env.inject(full(p.start_x), full(p.start_y), full(p.plat_default_x), full(p.plat_default_y))
         self.env.episode.zero_()
+        self.env.observe()                             # obs rows of the initial states
         self.games: List[DroneGameView] = [DroneGameView(self, i) for i in range(n)]
 
     def __len__(self) -> int:
@@ -113,33 +120,54 @@ class DroneGamePool:
     def __getitem__(self, i: int) -> "DroneGameView":
         return self.games[i]
 
-    # -- device work, one launch each -----------------------------------------------------------
+    def invalidate(self) -> None:
+        """Call after touching ``pool.env`` directly (set_state, inject, batched stepping)."""
+        with self._lock:
+            self.env.observe()
+            self._rec_ok = [False] * self.num_games
+
+    # -- device work --------------------------------------------------------------------------
+    def _record(self, i: int) -> List[float]:
+        """The DD_ENV_RECORD of game i (include/drone_b200.h dd_gather_env), fetched at most once per change."""
+        if not self._rec_ok[i]:
+            e = self.env
+            nv.check(e._lib.dd_gather_env(C.byref(e._state), e.obs.data_ptr(), e.obs_stride, e.reward.data_ptr(),
+                                          e.step_flags.data_ptr(), i, self.num_games, self._h_rec[i].data_ptr(),
+                                          e._stream()), "dd_gather_env")
+            torch.cuda.current_stream(e.device).synchronize()
+            self._rec_ok[i] = True
+        return self._h_rec[i].tolist()
+
     def _step_one(self, i: int, bits: int) -> Tuple[List[float], float, int]:
         with self._lock:
-            self._skip[i] = bits
-            obs, reward, flags = self.env.step_raw(self._skip, stats=False)
-            row, r, f = obs[i].tolist(), float(reward[i].item()), int(flags[i].item())
-            self._skip[i] = nv.ACT_SKIP
-        return row, r, f
+            self._h_act[i] = bits
+            self.env.step_raw(self._h_act, stats=False)    # every other game carries DD_ACT_SKIP
+            self._rec_ok[i] = False
+            rec = self._record(i)                          # synchronises: the action byte may be rewritten now
+            self._h_act[i] = nv.ACT_SKIP
+        return rec[:16], rec[16], int(rec[17])
 
     def _reset_one(self, i: int) -> List[float]:
         with self._lock:
-            self._mask.zero_()
-            self._mask[i] = 1
-            return self.env.reset(self._mask)[i].tolist()
+            e = self.env
+            self._h_mask.zero_()
+            self._h_mask[i] = 1
+            nv.check(e._lib.dd_reset(C.byref(e._state), C.byref(e.params), C.byref(e._cfg), self._h_mask.data_ptr(),
+                                     e.obs.data_ptr(), e.obs_stride, self.num_games, e._stream()), "dd_reset")
+            e._needs_reset = False
+            self._rec_ok[i] = False
+            return self._record(i)[:16]
 
     def _observe_one(self, i: int) -> List[float]:
         with self._lock:
-            return self.env.observe()[i].tolist()
+            return self._record(i)[:16]
 
     def _raw_one(self, i: int) -> Dict[str, float]:
         with self._lock:
-            e = self.env
-            pv, af, pf = e.pos_vel[i].tolist(), e.att_fuel[i].tolist(), e.platform[i].tolist()
-            return {"x": pv[0], "y": pv[1], "vx": pv[2], "vy": pv[3], "angle": af[0], "angular_velocity": af[1],
-                    "fuel": af[2], "total_reward": af[3], "platform_x": pf[0], "platform_y": pf[1],
-                    "steps": int(e.steps[i].item()), "episode": int(e.episode[i].item()) & 0xffffffff,
-                    "flags": int(e.flags[i].item())}
+            r = self._record(i)
+            return {"x": r[21], "y": r[22], "vx": r[23], "vy": r[24], "angle": r[25], "angular_velocity": r[26],
+                    "fuel": r[27], "total_reward": r[28], "platform_x": r[29], "platform_y": r[30],
+                    "steps": int(r[19]), "episode": int(r[20]) & 0xffffffff, "flags": int(r[18])}
 
 
 class DroneGameView:

@@ -308,6 +308,27 @@ __global__ void __launch_bounds__(kBlock) pack_actions_kernel(const uint8_t* a3,
     packed[i] = (uint8_t)((m ? DD_ACT_MAIN : 0u) | (l ? DD_ACT_LEFT : 0u) | (r ? DD_ACT_RIGHT : 0u));
 }
 
+// one env's observation row, last step outputs and raw state as doubles (compat layer: one copy per per-game step)
+template <typename R>
+__global__ void gather_env_kernel(const R* pos_vel, const R* att_fuel, const R* platform, const int32_t* steps,
+                                  const uint32_t* episode, const uint8_t* flags, const R* obs, int obs_stride,
+                                  const R* reward, const uint8_t* step_flags, int64_t i, double* out)
+{
+    const int j = threadIdx.x;
+    if (j >= DD_ENV_RECORD_DOUBLES) return;
+    double v = 0.0;
+    if (j < 16) v = obs ? (j < obs_stride ? (double)obs[i * obs_stride + j] : (double)steps[i]) : 0.0;
+    else if (j == 16) v = reward ? (double)reward[i] : 0.0;
+    else if (j == 17) v = step_flags ? (double)step_flags[i] : 0.0;
+    else if (j == 18) v = (double)flags[i];
+    else if (j == 19) v = (double)steps[i];
+    else if (j == 20) v = (double)episode[i];
+    else if (j < 25) v = (double)pos_vel[4 * i + (j - 21)];
+    else if (j < 29) v = (double)att_fuel[4 * i + (j - 25)];
+    else if (j < 31) v = (double)platform[2 * i + (j - 29)];
+    out[j] = v;
+}
+
 // out[0..5] = column sums of the slot copies; out[6] = out[5] (+ live steps, added by the next kernel)
 __global__ void stats_collapse_kernel(const unsigned long long* stats, unsigned long long* out)
 {
@@ -530,6 +551,25 @@ int dd_fill_random_actions(uint8_t* actions_tn, uint64_t seed, uint64_t env_id_b
     if (n < 0 || T < 0) return DD_E_RANGE;
     if (n == 0 || T == 0) return 0;
     dd::fill_random_actions_kernel<<<dd::grid_for(n, dd::kBlock), dd::kBlock, 0, (cudaStream_t)stream>>>(actions_tn, seed, env_id_base, t0, T, n);
+    return (int)cudaGetLastError();
+}
+
+int dd_gather_env(const DDState* s, const void* obs, int32_t obs_stride, const void* reward,
+                  const uint8_t* step_flags, int64_t i, int64_t n, double* out, void* stream)
+{
+    if (!s || !out) return DD_E_NULL;
+    if (!s->pos_vel || !s->att_fuel || !s->platform || !s->steps || !s->episode || !s->flags) return DD_E_NULL;
+    if (i < 0 || i >= n) return DD_E_RANGE;
+    if (obs && obs_stride != 15 && obs_stride != 16) return DD_E_RANGE;
+    if (s->dtype == DD_F32)
+        dd::gather_env_kernel<float><<<1, 32, 0, (cudaStream_t)stream>>>(
+            (const float*)s->pos_vel, (const float*)s->att_fuel, (const float*)s->platform, s->steps, s->episode, s->flags,
+            (const float*)obs, obs_stride, (const float*)reward, step_flags, i, out);
+    else if (s->dtype == DD_F64)
+        dd::gather_env_kernel<double><<<1, 32, 0, (cudaStream_t)stream>>>(
+            (const double*)s->pos_vel, (const double*)s->att_fuel, (const double*)s->platform, s->steps, s->episode, s->flags,
+            (const double*)obs, obs_stride, (const double*)reward, step_flags, i, out);
+    else return DD_E_DTYPE;
     return (int)cudaGetLastError();
 }
 
