@@ -198,6 +198,12 @@ int dd_normalize(const float *x, float *y, const double *moments, double eps, in
 int dd_gae(const float *rewards_tn, const float *values_t1n, const uint8_t *dones_tn, float *adv_tn,
            float *returns_tn, double gamma, double lambda, int32_t T, int64_t n, void *stream);
 
+/* compute_returns (Policy_Gradients.ipynb: G = r + gamma * G over reversed(rewards)) for [T][n] rewards; dones_tn
+ * (nullable) marks the steps that ended an episode: G restarts behind them.  float64 accumulation like the
+ * notebook's python floats, fp32 result. */
+int dd_discounted_returns(const float *rewards_tn, const uint8_t *dones_tn, float *returns_tn, double gamma,
+                          int32_t T, int64_t n, void *stream);
+
 /* ---- K5: fused policy rollout (Actor_Critic_PPO.ipynb c11, c16) ---------------------------- */
 /* fp32 parameters of DroneGamerBoi exactly as torch stores them: nn.Linear.weight is [out][in]
  * row-major; g / be are nn.LayerNorm weight / bias.  15-128-128-64-3. */

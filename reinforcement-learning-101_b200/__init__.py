@@ -14,7 +14,7 @@ from ._native import build_native
 from .distributed import (allreduce_moments, allreduce_stats, init_from_env, mean_std_from_moments, shard_range,
                           stats_dict)
 
-__all__ = ["native", "build_native", "BatchedDroneEnv", "StepInfo", "gae", "advantage_moments",
+__all__ = ["native", "build_native", "BatchedDroneEnv", "StepInfo", "gae", "discounted_returns", "advantage_moments",
            "normalize_advantages", "allreduce_stats", "allreduce_moments", "shard_range", "stats_dict",
            "mean_std_from_moments", "init_from_env", "PolicyBlob", "ValueBlob", "policy_forward", "value_forward",
            "rollout_values", "policy_rollout",
@@ -27,7 +27,7 @@ def __getattr__(name):
     if name in ("BatchedDroneEnv", "StepInfo"):
         from . import env
         return getattr(env, name)
-    if name in ("gae", "advantage_moments", "normalize_advantages"):
+    if name in ("gae", "discounted_returns", "advantage_moments", "normalize_advantages"):
         from . import ppo_ops
         return getattr(ppo_ops, name)
     if name in ("PolicyBlob", "ValueBlob", "policy_forward", "value_forward", "rollout_values", "policy_rollout"):

@@ -153,6 +153,8 @@ def lib():
     L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
     L.dd_policy_forward.restype = C.c_int
     L.dd_policy_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
+    L.dd_discounted_returns.restype = C.c_int
+    L.dd_discounted_returns.argtypes = [vp, vp, vp, C.c_double, i32, i64, vp]
     L.dd_gather_env.restype = C.c_int
     L.dd_gather_env.argtypes = [PS, vp, i32, vp, vp, i64, i64, vp, vp]
     L.dd_value_pack.restype = C.c_int
@@ -182,5 +184,5 @@ def default_params() -> DDParams:
 EXPORTS = (
     "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout", "dd_rollout_shaped",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
-    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env",
+    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env", "dd_discounted_returns",
 )

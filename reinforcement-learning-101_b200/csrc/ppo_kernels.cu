@@ -131,6 +131,36 @@ __global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict_
     }
 }
 
+// compute_returns (Policy_Gradients.ipynb: G = r + gamma * G over reversed(rewards), python floats = float64),
+// batched: G restarts after a step that ended an episode.  Accumulated in double like the original, written as
+// fp32 (the notebook builds a float32 tensor from the list).  Same chunked load scheme as gae_kernel.
+__global__ void __launch_bounds__(kGaeBlock) returns_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                            float* __restrict__ out, double gamma, int32_t T, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
+    if (i >= n) return;
+    double G = 0.0;
+    for (int32_t t1 = T; t1 > 0; t1 -= kGaeUnroll) {
+        float r[kGaeUnroll];
+        uint8_t d[kGaeUnroll];
+#pragma unroll
+        for (int j = 0; j < kGaeUnroll; ++j) {
+            const int32_t t = t1 - 1 - j;
+            const int64_t o = (int64_t)(t >= 0 ? t : 0) * n + i;
+            r[j] = __ldg(rew + o); d[j] = done ? __ldg(done + o) : (uint8_t)0;
+        }
+#pragma unroll
+        for (int j = 0; j < kGaeUnroll; ++j) {
+            const int32_t t = t1 - 1 - j;
+            if (t >= 0) {
+                if (d[j]) G = 0.0;                              // step t ended its episode: nothing flows back into it
+                G = __dadd_rn((double)r[j], __dmul_rn(gamma, G));
+                out[(int64_t)t * n + i] = (float)G;
+            }
+        }
+    }
+}
+
 static inline int wave_grid(int64_t work_items, int per_block, int max_waves_ctas)
 {
     int64_t g = (work_items + per_block - 1) / per_block;
@@ -173,6 +203,17 @@ int dd_gae(const float* rewards_tn, const float* values_t1n, const uint8_t* done
     const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
     dd::gae_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn,
                                                                        (float)gamma, (float)(gamma * lambda), T, n);
+    return (int)cudaGetLastError();
+}
+
+int dd_discounted_returns(const float* rewards_tn, const uint8_t* dones_tn, float* returns_tn, double gamma,
+                          int32_t T, int64_t n, void* stream)
+{
+    if (!rewards_tn || !returns_tn) return DD_E_NULL;
+    if (n < 0 || T < 0) return DD_E_RANGE;
+    if (n == 0 || T == 0) return 0;
+    const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
+    dd::returns_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, dones_tn, returns_tn, gamma, T, n);
     return (int)cudaGetLastError();
 }
 

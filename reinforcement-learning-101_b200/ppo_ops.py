@@ -52,6 +52,27 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma:
     return (adv, ret) if want_returns else adv
 
 
+def discounted_returns(rewards: torch.Tensor, dones: Optional[torch.Tensor] = None, gamma: float = 0.99,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``compute_returns`` of the policy-gradient notebook (G_t = r_t + gamma * G_{t+1}, float64 accumulation,
+    restarting behind every step whose ``dones`` byte is non-zero) for fp32 ``rewards`` [T,N]."""
+    _need(rewards, torch.float32, "rewards")
+    T, n = rewards.shape
+    if dones is not None:
+        _need(dones, torch.uint8, "dones")
+        if tuple(dones.shape) != (T, n):
+            raise ValueError("dones must be [T,N]")
+    if out is None:
+        out = torch.empty_like(rewards)
+    else:
+        _need(out, torch.float32, "out")
+        if tuple(out.shape) != (T, n):
+            raise ValueError("out must be [T,N]")
+    nv.check(nv.lib().dd_discounted_returns(rewards.data_ptr(), None if dones is None else dones.data_ptr(),
+                                            out.data_ptr(), float(gamma), T, n, _stream(rewards)), "dd_discounted_returns")
+    return out
+
+
 def advantage_moments(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """float64[3] on device: (n, sum x, sum x^2).  ACCUMULATES into ``out`` when given."""
     _need(x, torch.float32, "x")

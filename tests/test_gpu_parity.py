@@ -431,6 +431,37 @@ def test_gae_bit_exact(T, n):
 # =================================================================================================
 # BASELINE.json full size (1M envs): size-independent properties
 # =================================================================================================
+@pytest.mark.parametrize("T,n", [(1, 1), (37, 130), (250, 4099)])
+def test_discounted_returns_bit_exact(T, n):
+    """compute_returns of Policy_Gradients.ipynb (python-float loop G = r + gamma * G over reversed(rewards)),
+    per episode: float64 accumulation, fp32 result -- bit for bit."""
+    g = np.random.default_rng(T * 1000 + n)
+    rew = g.normal(0, 3, (T, n)).astype(np.float32)
+    done = (g.random((T, n)) < 0.02).astype(np.uint8)
+    exp = np.zeros((T, n), np.float32)
+    for i in range(min(n, 64)):                                  # the notebook's loop, episode by episode
+        G = 0.0
+        for t in reversed(range(T)):
+            if done[t, i]:
+                G = 0.0
+            G = float(rew[t, i]) + 0.99 * G
+            exp[t, i] = np.float32(G)
+    got = dd.discounted_returns(_t(rew), _t(done), gamma=0.99).cpu().numpy()
+    assert np.array_equal(got[:, :min(n, 64)], exp[:, :min(n, 64)])
+    # vectorised float64 check of every column, and the no-dones form
+    G = np.zeros(n); full = np.zeros((T, n), np.float32)
+    for t in reversed(range(T)):
+        G = np.where(done[t] != 0, 0.0, G)
+        G = rew[t].astype(np.float64) + 0.99 * G
+        full[t] = G.astype(np.float32)
+    assert np.array_equal(got, full)
+    nod = dd.discounted_returns(_t(rew), None, gamma=0.9).cpu().numpy()
+    G = np.zeros(n)
+    for t in reversed(range(T)):
+        G = rew[t].astype(np.float64) + 0.9 * G
+        assert np.array_equal(nod[t], G.astype(np.float32))
+
+
 def test_full_size_properties():
     n, T = 1 << 20, 300
     kw = dict(seed=0, randomize_drone=True, randomize_platform=True, max_steps=250, auto_reset=True, dtype=torch.float32)
