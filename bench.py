@@ -353,8 +353,11 @@ def run_ours(args):
 
     # ---- K5: fused policy rollout, BASELINE configs[3]: 65,536 envs x 250 steps, policy MLP in-kernel ----
     k5 = None
-    if not args.no_policy:
-        fix = os.path.join(ROOT, "tests", "golden", "policy_v1.npz")
+    fix = os.path.join(ROOT, "tests", "golden", "policy_v1.npz")
+    cfix_path = os.path.join(ROOT, "tests", "golden", "critic_v1.npz")
+    if not args.no_policy and not (os.path.exists(fix) and os.path.exists(cfix_path)):
+        k5 = {"skipped": "checkpoint fixtures tests/golden/policy_v1.npz / critic_v1.npz not found"}   # same on every rank
+    elif not args.no_policy:
         import numpy as np
         d = np.load(fix)
         sd = {kk: torch.from_numpy(d[kk]) for kk in d.files if kk.startswith("network")}
@@ -396,7 +399,7 @@ def run_ours(args):
         del fenv, fbuf
         # what follows the rollout in the PPO loop (Actor_Critic_PPO.ipynb, PHASE 2): critic values over the stored
         # states + bootstrap row, compute_gae, advantage normalisation -- all on the rollout buffers in HBM
-        cfix = np.load(os.path.join(ROOT, "tests", "golden", "critic_v1.npz"))
+        cfix = np.load(cfix_path)
         vblob = dd.ValueBlob({kk: torch.from_numpy(cfix[kk]) for kk in cfix.files if kk.startswith("network")}, device=dev)
         final_obs = penv.observe().clone()
         vals = dd.rollout_values(vblob, pbuf["obs"], final_obs)
