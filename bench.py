@@ -478,7 +478,8 @@ def run_ours(args):
                              f"({S} x ~{n * 116 >> 20} MiB state+outputs > 126 MB L2)",
                        "launch": f"CUDA graph of {G} step launches, replayed, {C_} parallel chain(s) over independent shards; launch_flags={args.launch_flags:#x}", "parallelism": f"env-sharded x{ws}, no per-step comms"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel<float,AUTO,OBS>", "achieved": achieved, "peak": peak_gbs,
-                         "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "unit": "GB/s", "frac": achieved / peak_gbs, "frac_of_nominal_8000_gbs": achieved / 8000.0,
+                         "traffic": traffic, "traffic_unit": "bytes per launch",
                          "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_GYM * n, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n},
             "variants": {
