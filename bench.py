@@ -351,6 +351,12 @@ def run_ours(args):
     ms_roll = timed(lambda: run_rollouts(S), lambda: run_rollouts(reps))
     launches += reps
 
+    def run_rollouts_bb(k):                                 # cfg 3 (ii): fixed policy main = vy > 1.5, computed in-kernel
+        for j in range(k):
+            envs[j % S].rollout(T_ROLL, "bangbang", t0=(j // S) * T_ROLL)
+    ms_roll_bb = timed(lambda: run_rollouts_bb(S), lambda: run_rollouts_bb(reps))
+    launches += reps
+
     # ---- K5: fused policy rollout, BASELINE configs[3]: 65,536 envs x 250 steps, policy MLP in-kernel ----
     k5 = None
     fix = os.path.join(ROOT, "tests", "golden", "policy_v1.npz")
@@ -486,6 +492,8 @@ def run_ours(args):
                 "step_only": {"value": n * K * ws / (so_ms * 1e-3), "ms_per_step": so_ms / K,
                               "algorithmic_bytes_per_env_step": BYTES_STEP_ONLY, "achieved_gbs": so_achieved,
                               "frac": so_achieved / peak_gbs},
+                "rollout_T50_fixed_policy_bangbang": {"value": n * T_ROLL * reps * ws / (ms_roll_bb * 1e-3),
+                                                      "ms_per_launch": ms_roll_bb / reps, "steps_per_launch": T_ROLL},
                 "rollout_T50_in_kernel_actions": {"value": n * T_ROLL * reps * ws / (ms_roll * 1e-3),
                                                   "ms_per_launch": ms_roll / reps, "steps_per_launch": T_ROLL},
                 "fused_policy_rollout": k5,
