@@ -420,6 +420,30 @@ def run_ours(args):
                 dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
         ms_tail = timed(lambda: run_ppo_tail(1), lambda: run_ppo_tail(reps_p))
         launches += 5 * reps_p
+        # the same through HOST-side inputs / outputs, as one PPO iteration sees it: policy + critic weights come from
+        # host state_dicts (packed and uploaded every iteration, like after an optimiser step), the rollout buffers
+        # stay in HBM for the learner, the episode statistics and advantage moments go back to the host
+        sd_host = {kk: v.clone() for kk, v in sd.items()}
+        sdc_host = {kk: torch.from_numpy(cfix[kk]) for kk in cfix.files if kk.startswith("network")}
+        t_it = []
+        for it in range(3 + reps_p):
+            barrier()
+            t0 = time.perf_counter()
+            b_it = dd.PolicyBlob(sd_host, device=dev)
+            vb_it = dd.ValueBlob(sdc_host, device=dev)
+            penv.reset_stats()
+            dd.policy_rollout(penv, b_it, TP, sample=True, t0=(100 + it) * TP, want="arldo", out=pbuf)
+            dd.rollout_values(vb_it, pbuf["obs"], penv.observe())
+            dd.gae(pbuf["reward"], vals, dones, out=adv)
+            dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
+            st_it = penv.stats(reduce=ws > 1)                  # device -> host: synchronises
+            t_it.append(time.perf_counter() - t0)
+        launches += 9 * len(t_it)
+        it_s = max_over_ranks(sum(t_it[3:]) / reps_p * 1e3) * 1e-3
+        k5["ppo_iteration_e2e"] = {"what": "host state_dicts -> pack + upload (policy, critic) -> fused rollout -> critic values -> GAE -> "
+                                           "advantage normalisation -> episode statistics back on the host; wall clock per iteration",
+                                   "ms": it_s * 1e3, "env_steps_per_s": NP * TP * ws / it_s,
+                                   "landing_rate": st_it["landing_rate"]}
         k5["ppo_data_path"] = {"what": "critic values [T+1,N] (tcgen05, persistent forward) + GAE + advantage normalisation on the rollout buffers",
                                "ms": ms_tail / reps_p, "samples_per_s": NP * TP * reps_p * ws / (ms_tail * 1e-3),
                                "rollout_plus_tail_ms": (ms_pol + ms_tail) / reps_p}
