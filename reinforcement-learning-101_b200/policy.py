@@ -47,10 +47,20 @@ class PolicyBlob:
                 key = key[len("network."):]                 # a bare nn.Sequential: '0.weight', ...
             if key not in state_dict:
                 raise KeyError(f"state_dict lacks {key!r} (expected the DroneGamerBoi layout)")
-            t = state_dict[key].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            t = state_dict[key].detach()
             if tuple(t.shape) != shape:
                 raise ValueError(f"{key}: shape {tuple(t.shape)} != {shape}")
             params.append(t)
+        if all(not t.is_cuda for t in params):
+            # host state_dict: one staging buffer and ONE host->device copy instead of 14 small ones
+            flat = torch.cat([t.to(torch.float32).reshape(-1) for t in params]).to(self.device)
+            offs = [0]
+            for t in params:
+                offs.append(offs[-1] + t.numel())
+            params = [flat[offs[j]:offs[j + 1]] for j in range(len(params))]    # every offset is a multiple of 4 bytes
+            self._flat = flat
+        else:
+            params = [t.to(device=self.device, dtype=torch.float32).contiguous() for t in params]
         self._params = params                              # keep alive until the pack kernel has run
         self.blob = torch.empty(BLOB_BYTES, dtype=torch.uint8, device=self.device)
         self.consts = nv.DDPolicyConsts()                  # host side: rides in the kernel-argument constant bank
