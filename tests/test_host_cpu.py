@@ -50,6 +50,26 @@ def test_header_constants_match_binding():
     assert fields == [k for k, _ in nv.DDParams._fields_]
 
 
+def test_policy_binding_matches_header():
+    """K5 binding constants: blob size, DDPolicyConsts image, per-game record length."""
+    import ctypes as C
+    h = _header()
+    pol = importlib.import_module("reinforcement-learning-101_b200.policy")
+    assert int(re.search(r"#define DD_POLICY_BLOB_BYTES (\d+)", h).group(1)) == pol.BLOB_BYTES
+    assert int(re.search(r"#define DD_ENV_RECORD_DOUBLES (\d+)", h).group(1)) == nv.ENV_RECORD_DOUBLES
+    body = re.search(r"typedef struct DDPolicyConsts \{(.*?)\} DDPolicyConsts;", h, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    floats = 0
+    for decl in re.findall(r"float ([^;]+);", body):
+        for f in decl.split(","):
+            n = 1
+            for d in re.findall(r"\[(\d+)\]", f):
+                n *= int(d)
+            floats += n
+    assert floats * 4 == C.sizeof(nv.DDPolicyConsts) == 836 * 4
+    assert C.sizeof(nv.DDPolicy) == 14 * C.sizeof(C.c_void_p)
+
+
 def test_default_params_are_the_reference_config(lib):
     """config.py:4-5,18-68 and game_engine.py:66-85,156-177,214,254."""
     p = nv.default_params()
