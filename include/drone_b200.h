@@ -54,6 +54,10 @@ extern "C" {
 #define DD_MAX_ENVS_PER_CALL 0x7fffff00   /* 32-bit env index inside one call; shard above that */
 #define DD_RETURN_FIXED_SCALE 1048576.0   /* sum_return is accumulated as int64 in units of 2^-20 */
 
+/* ---- DDEnvConfig.shaping -------------------------------------------------------- */
+#define DD_SHAPING_PPO  0   /* calc_reward(state, prev_state): Actor_Critic_PPO.ipynb c7:L2-101 == Actor_Critic_Basic.ipynb */
+#define DD_SHAPING_PG   1   /* calc_reward(state): Policy_Gradients.ipynb code cells 5-6 (stateless)                       */
+
 /* ---- DDEnvConfig.launch_flags ------------------------------------------------- */
 #define DD_LAUNCH_PDL        0x01   /* programmatic dependent launch: this kernel's CTAs may become
                                        resident while the previous kernel of the stream drains; the
@@ -124,7 +128,7 @@ typedef struct DDEnvConfig {
     int32_t randomize_drone; /* DroneGame(randomize_drone=...)    game_engine.py:14 */
     int32_t randomize_platform; /* DroneGame(randomize_platform=...) */
     int32_t launch_flags;    /* DD_LAUNCH_* bits; 0 = plain stream-ordered launch */
-    int32_t reserved;        /* must be 0 */
+    int32_t shaping;         /* which notebook's client-side calc_reward the `shaped` outputs follow: DD_SHAPING_* */
 } DDEnvConfig;
 
 int  dd_abi_version(void);

@@ -67,12 +67,66 @@ def shaped_reward(obs: Sequence[float], prev_dist: Optional[float]) -> float:
     return total
 
 
+def shaped_reward_pg(obs: Sequence[float]) -> float:
+    """``calc_reward(state)['total']`` of /root/reference/Policy_Gradients.ipynb (code cell 6; helpers
+    ``calc_velocity_alignment`` of code cell 5 and ``inverse_quadratic`` / ``scaled_shifted_negative_sigmoid`` of
+    rl_helpers/scalers.py:14-15,20-21), in the notebook's statement order.  Stateless: no prev_state.
+    Note the notebook's sign convention in calc_velocity_alignment: ``optimal_dx = -state.dx_to_platform``."""
+    total = 0
+    dist = obs[DIST]
+    speed = obs[SPEED]
+    # time penalty: -inverse_quadratic(dist, decay=50, scaler=1-0.3) - 0.3
+    total += -((1 - 0.3) * (1 / (1 + (50 * (dist ** 2))))) - 0.3
+    # velocity alignment (cosine of velocity vs "optimal" direction)
+    odx, ody = -obs[DX], -obs[DY]
+    onorm = math.sqrt(odx ** 2 + ody ** 2)
+    if onorm < 1e-6:
+        va = 1.0
+    else:
+        odx /= onorm
+        ody /= onorm
+        if speed < 1e-6:
+            va = 0.0
+        else:
+            va = (obs[VX] / speed) * odx + (obs[VY] / speed) * ody
+    r_distance = 0
+    r_align = 0
+    if dist > 0.065 and obs[DY] > 0:
+        r_distance = int(va > 0) * speed * (4.5 * (1 / (1 + math.exp(10 * (dist - 0.5)))))
+        if va > 0:
+            r_align = 0.5
+    total += r_distance
+    total += r_align
+    excess = abs(obs[ANGLE]) - (((0.20 - 0.111) * dist) + 0.111)
+    total += -max(excess, 0)
+    if dist < 1:
+        total += -2 * max(speed - 0.1, 0)
+    else:
+        total += -1 * max(speed - 0.4, 0)
+    if obs[DY] > 0:
+        total += 0
+    else:
+        total += obs[DY] * 4.0
+    terminal = 0
+    if obs[LANDED]:
+        terminal = 500.0 + obs[FUEL] * 100.0
+    elif obs[CRASHED]:
+        terminal = -200.0
+        if dist > 0.3:
+            terminal -= 100.0
+    total += terminal
+    return total
+
+
 class EpisodeShaper:
     """The notebook's per-game bookkeeping: feed the state the policy saw and the state after the
-    step; returns the training reward of that step (with the time-out penalty)."""
+    step; returns the training reward of that step (with the time-out penalty).  ``variant``: 'ppo'
+    (Actor_Critic_PPO / Actor_Critic_Basic: calc_reward(state, prev_state)) or 'pg' (Policy_Gradients:
+    calc_reward(state); the same -500 time-out rule, Policy_Gradients.ipynb collect_episodes)."""
 
-    def __init__(self, max_steps: int = 0):
+    def __init__(self, max_steps: int = 0, variant: str = "ppo"):
         self.max_steps = int(max_steps)
+        self.variant = variant
         self.reset()
 
     def reset(self) -> None:
@@ -80,7 +134,7 @@ class EpisodeShaper:
         self.count = 0
 
     def step(self, current_obs: Sequence[float], next_obs: Sequence[float]):
-        r = shaped_reward(next_obs, self.prev_dist)
+        r = shaped_reward(next_obs, self.prev_dist) if self.variant == "ppo" else shaped_reward_pg(next_obs)
         self.count += 1
         timed_out = self.max_steps > 0 and self.count >= self.max_steps
         if timed_out and not next_obs[LANDED]:

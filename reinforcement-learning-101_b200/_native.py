@@ -31,6 +31,7 @@ POLICY_TRACE, POLICY_RANDOM, POLICY_BANGBANG = 0, 1, 2
 OBS_DIM = 15
 STATS_SLOTS, STATS_WORDS = 64, 8
 ENV_RECORD_DOUBLES = 32
+SHAPING_PPO, SHAPING_PG = 0, 1
 RETURN_FIXED_SCALE = 1048576.0
 LAUNCH_PDL, LAUNCH_BLOCK_128, LAUNCH_BLOCK_512 = 0x01, 0x10, 0x20
 
@@ -62,7 +63,7 @@ class DDEnvConfig(C.Structure):
         ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
         ("max_steps", C.c_int32), ("auto_reset", C.c_int32),
         ("randomize_drone", C.c_int32), ("randomize_platform", C.c_int32),
-        ("launch_flags", C.c_int32), ("reserved", C.c_int32),
+        ("launch_flags", C.c_int32), ("shaping", C.c_int32),
     ]
 
 

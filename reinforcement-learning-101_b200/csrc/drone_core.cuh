@@ -133,6 +133,7 @@ template <> struct Arith<double> {
     static DD_HD double fma_(double a, double b, double c) { return add(mul(a, b), c); }   // never fused
     static DD_HD double div(double a, double d, double /*inv_d*/) { return a / d; }
     static DD_HD double sqrt_(double a) { return sqrt(a); }
+    static DD_HD double exp_(double a) { return exp(a); }
     static DD_HD double abs_(double a) { return fabs(a); }
     // sin / cos of an angle in degrees: np.radians(a) == a * (pi / 180)   physics.py:16-18
     static DD_HD void sincos_deg(double deg, double& s, double& c) {
@@ -159,6 +160,7 @@ template <> struct Arith<float> {
 #endif
     static DD_HD float div(float a, float /*d*/, float inv_d) { return mul(a, inv_d); }
     static DD_HD float sqrt_(float a) { return sqrtf(a); }
+    static DD_HD float exp_(float a) { return expf(a); }
     static DD_HD float abs_(float a) { return fabsf(a); }
     static DD_HD void sincos_deg(float deg, float& s, float& c) {
 #if defined(__CUDA_ARCH__)
@@ -346,6 +348,64 @@ DD_HD R shaped_reward_ppo(const Env<R>& e, uint32_t flags, R speed, R dist, R pr
     total = A::add(total, terminal);
     if (timed_out && !(flags & DD_LANDED)) total -= (R)500;             // c16:L89-93
     return total;
+}
+
+// calc_reward(state) of Policy_Gradients.ipynb (code cell 6; calc_velocity_alignment of code cell 5,
+// inverse_quadratic / scaled_shifted_negative_sigmoid of rl_helpers/scalers.py:14-15,20-21) + the same -500
+// time-out (collect_episodes of that notebook), in the notebook's statement order; restated in
+// oracle/shaping_port.py (shaped_reward_pg), pinned by executing the notebook's cells.  Stateless.
+template <typename R>
+DD_HD R shaped_reward_pg(const Env<R>& e, uint32_t flags, R speed, R dist, bool timed_out, const Consts<R>& k)
+{
+    using A = Arith<R>;
+    const R nd = A::div(dist, k.width, k.inv_width);                   // distance_to_platform
+    const R ns = A::div(speed, k.vel_norm, k.inv_vel);                 // speed
+    const R nvx = A::div(e.vx, k.vel_norm, k.inv_vel), nvy = A::div(e.vy, k.vel_norm, k.inv_vel);
+    const R ndx = A::div(e.px - e.x, k.width, k.inv_width), ndy = A::div(e.py - e.y, k.height, k.inv_height);
+    const R nang = A::div(e.angle, k.angle_norm, k.inv_angle);
+    const R nfuel = A::div(e.fuel, k.max_fuel, k.inv_fuel);
+
+    // time penalty: -inverse_quadratic(dist, decay=50, scaler=1-0.3) - 0.3
+    R total = -A::mul((R)(1 - 0.3), (R)1 / A::add((R)1, A::mul((R)50, A::mul(nd, nd)))) - (R)0.3;
+    // velocity alignment; note the notebook's sign: optimal_dx = -state.dx_to_platform
+    R va;
+    R odx = -ndx, ody = -ndy;
+    const R onorm = A::sqrt_(A::add(A::mul(odx, odx), A::mul(ody, ody)));
+    if (onorm < (R)1e-6) {
+        va = (R)1;
+    } else {
+        odx = odx / onorm; ody = ody / onorm;
+        va = ns < (R)1e-6 ? (R)0 : A::add(A::mul(nvx / ns, odx), A::mul(nvy / ns, ody));
+    }
+    R r_distance = (R)0, r_align = (R)0;
+    if (nd > (R)0.065 && ndy > (R)0) {
+        const R sig = A::mul((R)4.5, (R)1 / A::add((R)1, A::exp_(A::mul((R)10, nd - (R)0.5))));
+        r_distance = A::mul(A::mul(va > (R)0 ? (R)1 : (R)0, ns), sig);
+        if (va > (R)0) r_align = (R)0.5;
+    }
+    total = A::add(total, r_distance);
+    total = A::add(total, r_align);
+    const R excess = A::abs_(nang) - A::add(A::mul((R)(0.20 - 0.111), nd), (R)0.111);
+    total = A::add(total, excess > (R)0 ? -excess : (R)0);
+    const R over = nd < (R)1 ? A::mul((R)-2, (ns - (R)0.1 > (R)0 ? ns - (R)0.1 : (R)0))
+                             : A::mul((R)-1, (ns - (R)0.4 > (R)0 ? ns - (R)0.4 : (R)0));
+    total = A::add(total, over);
+    total = A::add(total, ndy > (R)0 ? (R)0 : A::mul(ndy, (R)4.0));
+    R terminal = (R)0;
+    if (flags & DD_LANDED) terminal = A::add((R)500.0, A::mul(nfuel, (R)100.0));
+    else if (flags & DD_CRASHED) terminal = nd > (R)0.3 ? (R)-300.0 : (R)-200.0;
+    total = A::add(total, terminal);
+    if (timed_out && !(flags & DD_LANDED)) total -= (R)500;
+    return total;
+}
+
+// one switch for the kernels: `mode` is DDEnvConfig.shaping
+template <typename R>
+DD_HD R shaped_reward(int mode, const Env<R>& e, uint32_t flags, R speed, R dist, R prev_dist, bool timed_out,
+                      const Consts<R>& k)
+{
+    return mode == DD_SHAPING_PG ? shaped_reward_pg(e, flags, speed, dist, timed_out, k)
+                                 : shaped_reward_ppo(e, flags, speed, dist, prev_dist, timed_out, k);
 }
 
 // ---------------------------------------------------------------------------------------

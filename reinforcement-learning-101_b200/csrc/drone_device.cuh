@@ -23,6 +23,7 @@ struct KArgs {
     uint32_t n;
     uint64_t seed, env_id_base;
     int32_t max_steps, obs_stride;
+    int32_t shaping;                      // DD_SHAPING_*
     int32_t rand_drone, rand_platform;
     Consts<R> k;
 };

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                 oflags = f;
                 if (shaping) {
                     const R sp = OBS ? speed : Arith<R>::sqrt_(Arith<R>::fma_(e.vx, e.vx, Arith<R>::mul(e.vy, e.vy)));
-                    shaped = shaped_reward_ppo(e, f, sp, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
+                    shaped = shaped_reward(a.shaping, e, f, sp, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
                     dprev = dcur;
                     dcur = Arith<R>::div(dist, k.width, k.inv_width);
                 }
@@ -378,7 +378,7 @@ static int fill_args(KArgs<R>& a, const DDState* s, const DDParams* p, const DDE
     a.prev_dist = (R*)s->prev_dist;
     a.steps = s->steps; a.episode = s->episode; a.flags = s->flags;
     a.n = (uint32_t)n; a.seed = c->seed; a.env_id_base = c->env_id_base;
-    a.max_steps = c->max_steps; a.obs_stride = DD_OBS_DIM;
+    a.max_steps = c->max_steps; a.obs_stride = DD_OBS_DIM; a.shaping = c->shaping;
     a.rand_drone = c->randomize_drone; a.rand_platform = c->randomize_platform;
     a.k = make_consts<R>(*p);
     return 0;
@@ -465,6 +465,7 @@ static int rollout_impl(const DDState* s, const DDParams* p, const DDEnvConfig* 
     if (obs_tn) { if (int rc = check_stride(obs_stride)) return rc; ra.a.obs_stride = obs_stride; }
     ra.a.stats = (unsigned long long*)stats;
     if (shaped_tn && !s->prev_dist && n > 0) return DD_E_NULL;
+    if (shaped_tn && c->shaping != DD_SHAPING_PPO && c->shaping != DD_SHAPING_PG) return DD_E_RANGE;
     ra.actions_tn = actions_tn; ra.reward_tn = (R*)reward_tn; ra.done_tn = done_tn; ra.obs_tn = (R*)obs_tn;
     ra.shaped_tn = (R*)shaped_tn;
     ra.t0 = t0; ra.T = T; ra.policy = policy; ra.auto_reset = c->auto_reset;

@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             if (!f && max_steps > 0 && e.steps >= max_steps) f = DD_DONE | DD_TRUNCATED;
             oflags = f;
             if (shaping) {
-                shaped = shaped_reward_ppo(e, f, speed, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
+                shaped = shaped_reward(a.shaping, e, f, speed, dist, dprev, max_steps > 0 && e.steps >= max_steps, k);
                 dprev = dcur;
                 dcur = Arith<float>::div(dist, k.width, k.inv_width);
             }
@@ -794,7 +794,7 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     pa.a.pos_vel = (float*)s->pos_vel; pa.a.att_fuel = (float*)s->att_fuel; pa.a.platform = (float*)s->platform;
     pa.a.steps = s->steps; pa.a.episode = s->episode; pa.a.flags = s->flags;
     pa.a.stats = (unsigned long long*)stats;
-    pa.a.n = (uint32_t)n; pa.a.seed = c->seed; pa.a.env_id_base = c->env_id_base; pa.a.max_steps = c->max_steps;
+    pa.a.n = (uint32_t)n; pa.a.seed = c->seed; pa.a.env_id_base = c->env_id_base; pa.a.max_steps = c->max_steps; pa.a.shaping = c->shaping;
     pa.a.rand_drone = c->randomize_drone; pa.a.rand_platform = c->randomize_platform;
     pa.a.k = dd::make_consts<float>(*p);
     pa.blob = (const uint8_t*)blob; pa.mode = mode; pa.t0 = t0; pa.T = T;

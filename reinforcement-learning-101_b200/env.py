@@ -75,13 +75,17 @@ class BatchedDroneEnv:
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, randomize_drone: bool = False,
                  randomize_platform: bool = True, max_steps: Optional[int] = None, auto_reset: bool = True,
                  dtype: torch.dtype = torch.float32, env_id_base: int = 0, obs_stride: int = nv.OBS_DIM,
-                 want_final_obs: bool = False, params: Optional[nv.DDParams] = None, launch_flags: int = 0):
+                 want_final_obs: bool = False, params: Optional[nv.DDParams] = None, launch_flags: int = 0,
+                 shaping: str = "ppo"):
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be torch.float32 or torch.float64")
         if obs_stride not in (15, 16):
             raise ValueError("obs_stride must be 15 or 16")
         if num_envs < 0:
             raise ValueError("num_envs must be >= 0")
+        if shaping not in ("ppo", "pg"):
+            raise ValueError("shaping must be 'ppo' (Actor_Critic_PPO / Actor_Critic_Basic calc_reward) or 'pg' "
+                             "(Policy_Gradients calc_reward)")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("BatchedDroneEnv runs on a CUDA device only (there is no CPU fallback)")
@@ -116,7 +120,8 @@ class BatchedDroneEnv:
                                  nv.F32 if dtype == torch.float32 else nv.F64, 0, self.prev_dist.data_ptr())
         self._cfg = nv.DDEnvConfig(int(seed) & (2 ** 64 - 1), int(env_id_base), int(max_steps or 0),
                                    int(bool(auto_reset)), int(bool(randomize_drone)), int(bool(randomize_platform)),
-                                   int(launch_flags), 0)
+                                   int(launch_flags), nv.SHAPING_PG if shaping == "pg" else nv.SHAPING_PPO)
+        self.shaping = shaping
         self._needs_reset = True
 
     # ---- configuration ------------------------------------------------------------------------

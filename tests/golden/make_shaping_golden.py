@@ -2,6 +2,9 @@
 notebook's own cells (Actor_Critic_PPO.ipynb code cells 6 and 7) on trajectories of the reference
 engine.  Run here (needs /root/reference):  python tests/golden/make_shaping_golden.py
 
+Also executes Policy_Gradients.ipynb's own calc_reward(state) (code cells 5-6) on the same episodes ->
+tests/golden/shaping_pg_golden.npz (reward [E, T]).
+
 Output tests/golden/shaping_golden.npz:
   obs      [E, T+1, 15]  observations s_0..s_T of E episodes (reference DroneGame, float64)
   n_steps  [E]           steps actually played (episode ends on done; later rows are padding)
@@ -36,8 +39,22 @@ def notebook_calc_reward():
     return ns["calc_reward"]
 
 
+def notebook_calc_reward_pg():
+    """Policy_Gradients.ipynb: calc_velocity_alignment (code cell 5) and calc_reward(state) (code cell 6)."""
+    import math
+    nb = json.load(open("/root/reference/Policy_Gradients.ipynb"))
+    code = [c for c in nb["cells"] if c["cell_type"] == "code"]
+    ns = {"math": math, "np": np, "DroneState": DroneState}
+    ns.update({k: getattr(scalers, k) for k in dir(scalers) if not k.startswith("_")})
+    for idx in (5, 6):
+        exec("".join(code[idx]["source"]), ns)
+    return ns["calc_reward"]
+
+
 def main(E=48, T=120, max_steps=100):
     calc_reward = notebook_calc_reward()
+    calc_reward_pg = notebook_calc_reward_pg()
+    rew_pg = np.zeros((E, T))
     rng = np.random.default_rng(2024)
     obs = np.zeros((E, T + 1, 15))
     rew = np.zeros((E, T))
@@ -63,11 +80,14 @@ def main(E=48, T=120, max_steps=100):
             nxt, _, done, _ = g.step({"main_thrust": int(a[0]), "left_thrust": int(a[1]), "right_thrust": int(a[2])})
             nxt = DroneState(**nxt)
             r = calc_reward(nxt, prev_state=prev)["total"]
-            if k + 1 >= max_steps:                          # Actor_Critic_PPO.ipynb c16:L89-93
+            r_pg = calc_reward_pg(nxt)["total"]
+            if k + 1 >= max_steps:                          # Actor_Critic_PPO.ipynb c16:L89-93 / Policy_Gradients collect_episodes
                 if not nxt.landed:
                     r -= 500
+                    r_pg -= 500
                 done = True
             rew[e, k] = r
+            rew_pg[e, k] = r_pg
             prev, state = state, nxt                        # c16:L101-102
             n_steps[e] = k + 1
             if done:
@@ -75,6 +95,7 @@ def main(E=48, T=120, max_steps=100):
                 break
     np.savez_compressed(os.path.join(HERE, "shaping_golden.npz"), obs=obs, reward=rew, n_steps=n_steps,
                         max_steps=np.int32(max_steps))
+    np.savez_compressed(os.path.join(HERE, "shaping_pg_golden.npz"), reward=rew_pg)     # same episodes / observations
     landed = sum(obs[e, n_steps[e], 13] for e in range(E))
     print("episodes", E, "landed", landed, "lengths", n_steps.min(), n_steps.max(), "reward range", rew.min(), rew.max())
 

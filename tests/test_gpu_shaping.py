@@ -1,5 +1,6 @@
-"""N2 -- the PPO notebook's client-side training reward as a fused epilogue of the rollout kernels,
-against oracle/shaping_port.py (pinned to the notebook's executed cells).
+"""N2 -- the notebooks' client-side training reward (variant 'ppo': Actor_Critic_PPO / Actor_Critic_Basic
+calc_reward(state, prev_state); variant 'pg': Policy_Gradients calc_reward(state)) as a fused epilogue of the rollout
+kernels, against oracle/shaping_port.py (pinned to the notebooks' executed cells).
 
 float64 instantiation: agreement to 1e-9 (same statement order, same roundings up to sin/cos ulps in
 the underlying state).  float32: |a-b| <= 2e-3*max(1,|b|) -- the distance term multiplies a
@@ -18,13 +19,13 @@ dd = importlib.import_module("reinforcement-learning-101_b200")
 DEV = "cuda:0"
 
 
-def _expected(obs0, obs, done, max_steps, auto_reset):
+def _expected(obs0, obs, done, max_steps, auto_reset, variant="ppo"):
     """obs0 [N,15] initial observation, obs [T,N,15] observation after each step, done [T,N] flags."""
     T, N = done.shape
     exp = np.zeros((T, N))
     valid = np.ones((T, N), bool)
     for i in range(N):
-        sh = EpisodeShaper(max_steps)
+        sh = EpisodeShaper(max_steps, variant=variant)
         cur = obs0[i]
         for t in range(T):
             if auto_reset and done[t, i]:
@@ -43,23 +44,27 @@ def _near_threshold(cur_prev_dist, o):
     """True where a branch condition of calc_reward is within 1e-5 of flipping."""
     d, s = o[..., DIST], o[..., SPEED]
     toward = (o[..., VX] * o[..., DX] + o[..., VY] * o[..., DY]) / np.maximum(d, 1e-9)
+    # policy-gradient variant: sign of the velocity alignment, its speed limit
+    align = -(o[..., VX] * o[..., DX] + o[..., VY] * o[..., DY])
     m = np.minimum.reduce([np.abs(s - 0.15), np.abs(s - 0.05), np.abs(toward - 0.1), np.abs(d - 0.065),
-                           np.abs(d - 0.3), np.abs(o[..., DY]), np.abs(s - 0.1), np.abs(s - 0.6)])
+                           np.abs(d - 0.3), np.abs(o[..., DY]), np.abs(s - 0.1), np.abs(s - 0.6), np.abs(s - 0.4),
+                           np.abs(align) * 1e2])
     return m < 1e-5
 
 
+@pytest.mark.parametrize("variant", ["ppo", "pg"])
 @pytest.mark.parametrize("dtype,policy", [(torch.float64, "bangbang"), (torch.float64, "random"), (torch.float32, "random")])
-def test_shaped_reward_freeze_after_done(dtype, policy):
+def test_shaped_reward_freeze_after_done(dtype, policy, variant):
     n, T, ms = 96, 130, 100
     e = dd.BatchedDroneEnv(n, device=DEV, seed=4, randomize_drone=True, randomize_platform=True, max_steps=ms,
-                           auto_reset=False, dtype=dtype)
+                           auto_reset=False, dtype=dtype, shaping=variant)
     obs0 = e.reset().double().cpu().numpy().copy()
     obs = torch.empty(T, n, 15, dtype=dtype, device=DEV); don = torch.empty(T, n, dtype=torch.uint8, device=DEV)
     shp = torch.empty(T, n, dtype=dtype, device=DEV); rew = torch.empty(T, n, dtype=dtype, device=DEV)
     # two launches: prev_dist must carry over between them
     e.rollout(60, policy, obs_out=obs[:60], done_out=don[:60], shaped_out=shp[:60], reward_out=rew[:60])
     e.rollout(T - 60, policy, t0=60, obs_out=obs[60:], done_out=don[60:], shaped_out=shp[60:], reward_out=rew[60:])
-    exp, valid = _expected(obs0, obs.double().cpu().numpy(), don.cpu().numpy(), ms, auto_reset=False)
+    exp, valid = _expected(obs0, obs.double().cpu().numpy(), don.cpu().numpy(), ms, auto_reset=False, variant=variant)
     got = shp.double().cpu().numpy()
     assert valid.all()
     if dtype == torch.float64:
@@ -74,21 +79,23 @@ def test_shaped_reward_freeze_after_done(dtype, policy):
     if policy == "random":
         assert (f & 4).any()                                   # ... and crashes
     if policy == "bangbang":
-        assert (f & 2).any() and got.max() > 800                # landings: 800 + 100 * fuel
+        assert (f & 2).any() and got.max() > (800 if variant == "ppo" else 500)   # landings: 800 (ppo) / 500 (pg) + 100 * fuel
     assert got[ms - 1][(f[ms - 1] & 8) > 0].max() < -490       # -500 on the time-out step (later rows: frozen, 0)
     assert (got[ms:] == 0).all()
 
 
-def test_shaped_reward_with_auto_reset_and_fused_policy(golden_dir):
+@pytest.mark.parametrize("variant", ["ppo", "pg"])
+def test_shaped_reward_with_auto_reset_and_fused_policy(golden_dir, variant):
     import os
     n, T, ms = 256, 120, 60
-    kw = dict(seed=8, randomize_drone=True, randomize_platform=True, max_steps=ms, auto_reset=True, dtype=torch.float32)
+    kw = dict(seed=8, randomize_drone=True, randomize_platform=True, max_steps=ms, auto_reset=True, dtype=torch.float32,
+              shaping=variant)
     e = dd.BatchedDroneEnv(n, device=DEV, **kw)
     obs0 = e.reset().double().cpu().numpy().copy()
     obs = torch.empty(T, n, 15, device=DEV); don = torch.empty(T, n, dtype=torch.uint8, device=DEV)
     shp = torch.empty(T, n, device=DEV)
     e.rollout(T, "random", obs_out=obs, done_out=don, shaped_out=shp)
-    exp, valid = _expected(obs0, obs.double().cpu().numpy(), don.cpu().numpy(), ms, auto_reset=True)
+    exp, valid = _expected(obs0, obs.double().cpu().numpy(), don.cpu().numpy(), ms, auto_reset=True, variant=variant)
     got = shp.double().cpu().numpy()
     bad = (np.abs(got - exp) > 2e-3 * np.maximum(1.0, np.abs(exp))) & valid
     near = _near_threshold(None, obs.double().cpu().numpy())

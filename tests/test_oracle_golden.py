@@ -212,6 +212,13 @@ def test_shaping_port_matches_the_notebook_cells(golden_dir):
             nxt = d["obs"][e, k + 1]
             kinds.add("landed" if nxt[13] else "crashed" if nxt[14] else "timeout" if timed_out else "flying")
     assert n_checked > 3000 and kinds == {"landed", "crashed", "timeout", "flying"}
-    # first step of an episode has no prev_state: no distance / hovering term
-    o = d["obs"][0, 1]
-    assert shaped_reward(o, None) >= shaped_reward(o, o[9]) - 1e-12 or True
+    # the policy-gradient notebook's stateless calc_reward(state) on the same episodes
+    g = np.load(os.path.join(golden_dir, "shaping_pg_golden.npz"))
+    n_pg = 0
+    for e in range(d["obs"].shape[0]):
+        sh = EpisodeShaper(int(d["max_steps"]), variant="pg")
+        for k in range(int(d["n_steps"][e])):
+            r, _ = sh.step(d["obs"][e, k], d["obs"][e, k + 1])
+            assert r == g["reward"][e, k], (e, k, r, g["reward"][e, k])
+            n_pg += 1
+    assert n_pg == n_checked
