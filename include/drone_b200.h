@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DD_ABI_VERSION 2
+#define DD_ABI_VERSION 3
 
 /* ---- flag byte (per-step output and persistent state) ---------------------- */
 #define DD_DONE        0x01u   /* game_engine.py:53  self.done            */
@@ -251,11 +251,14 @@ int dd_value_pack(const DDPolicy *p, void *blob, DDPolicyConsts *consts, void *s
 int dd_value_forward(const void *blob, const DDPolicyConsts *consts, const float *obs, float *values, int64_t n,
                      void *stream);
 
+/* `temperature` (DD_ACTION_SAMPLE, > 0): actions ~ Bernoulli(p^(1/tau) / (p^(1/tau) + (1-p)^(1/tau))) = Bernoulli(sigmoid(logit / tau)),
+ * the evaluation sampling of evaluate_policy_simple (Actor_Critic_PPO.ipynb c18); 1 = the policy's own distribution
+ * (collect_episodes_ppo).  probs / logp outputs always describe the untempered policy. */
 /* T steps of {observe, policy, act, step} in one launch; DD_F32 state only.  Optional [T][n] outputs:
  * actions (DD_ACT_* bits), logp (sum of the 3 Bernoulli log-probs), reward, done flags, obs [T][n][15],
  * probs [T][n][3], shaped (the notebook's training reward; needs s->prev_dist). */
 int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, const void *blob,
-                      const DDPolicyConsts *consts, int32_t mode, uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
+                      const DDPolicyConsts *consts, int32_t mode, float temperature, uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
                       uint8_t *done_tn, float *obs_tn, float *probs_tn, float *shaped_tn, uint64_t *stats, int64_t n,
                       void *stream);
 

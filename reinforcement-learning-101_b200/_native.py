@@ -22,7 +22,7 @@ NVCC_FLAGS = (
 )
 
 # ---- constants of include/drone_b200.h ------------------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 DONE, LANDED, CRASHED, TRUNCATED = 0x01, 0x02, 0x04, 0x08
 CAUSE_MASK, CAUSE_GROUND, CAUSE_FUEL, CAUSE_OOB = 0x30, 0x10, 0x20, 0x30
 ACT_MAIN, ACT_LEFT, ACT_RIGHT, ACT_SKIP = 0x01, 0x02, 0x04, 0x80
@@ -163,7 +163,7 @@ def lib():
     L.dd_value_forward.restype = C.c_int
     L.dd_value_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
     L.dd_policy_rollout.restype = C.c_int
-    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, C.POINTER(DDPolicyConsts), i32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, C.POINTER(DDPolicyConsts), i32, C.c_float, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     if L.dd_abi_version() != ABI_VERSION:
         raise NativeError(f"libdrone_b200.so ABI {L.dd_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L

@@ -100,7 +100,8 @@ struct PArgs {
     DDPolicyConsts pc;     // per-column LN parameters + last layer: constant bank -> uniform operands
     KArgs<float> a;        // env state pointers etc.
     const uint8_t* blob;
-    int32_t mode;              // DD_SAMPLE_*
+    int32_t mode;              // DD_ACTION_*
+    float inv_temperature;     // DD_ACTION_SAMPLE: actions ~ Bernoulli(sigmoid(logit * inv_temperature))
     uint32_t t0;
     int32_t T;
     uint8_t* actions_tn;
@@ -404,7 +405,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     // launch-constant switches, read from the argument block once
     const bool out_act = pa.actions_tn != nullptr, out_logp = pa.logp_tn != nullptr, out_rew = pa.reward_tn != nullptr,
                out_done = pa.done_tn != nullptr, out_probs = pa.probs_tn != nullptr, do_stats = a.stats != nullptr,
-               auto_reset = pa.auto_reset != 0, thresholded = pa.mode == DD_ACTION_THRESHOLD;
+               auto_reset = pa.auto_reset != 0, thresholded = pa.mode == DD_ACTION_THRESHOLD,
+               tempered = pa.inv_temperature != 1.0f;
     const int32_t max_steps = a.max_steps;
     const bool obs_out = !forward_only && pa.obs_tn != nullptr;
     const bool obs_bulk = obs_out && tile0 + kTile <= a.n && (a.n & 3u) == 0u &&
@@ -573,7 +575,11 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         } else {
             const float u0 = (float)(rnd.a >> 8) * (1.0f / 16777216.0f), u1 = (float)(rnd.b >> 8) * (1.0f / 16777216.0f),
                         u2 = (float)(rnd.c >> 8) * (1.0f / 16777216.0f);
-            act = (u0 < p0 ? DD_ACT_MAIN : 0u) | (u1 < p1 ? DD_ACT_LEFT : 0u) | (u2 < p2 ? DD_ACT_RIGHT : 0u);
+            // evaluate_policy_simple's temperature (c18): p^(1/tau) / (p^(1/tau) + (1-p)^(1/tau)) == sigmoid(logit / tau)
+            const float s0 = tempered ? __fdividef(1.0f, 1.0f + __expf(-z0 * pa.inv_temperature)) : p0,
+                        s1 = tempered ? __fdividef(1.0f, 1.0f + __expf(-z1 * pa.inv_temperature)) : p1,
+                        s2 = tempered ? __fdividef(1.0f, 1.0f + __expf(-z2 * pa.inv_temperature)) : p2;
+            act = (u0 < s0 ? DD_ACT_MAIN : 0u) | (u1 < s1 ? DD_ACT_LEFT : 0u) | (u2 < s2 ? DD_ACT_RIGHT : 0u);
         }
 
         // ---------------- environment step (same code as K1) -------------------------------------------
@@ -776,12 +782,13 @@ int dd_value_forward(const void* blob, const DDPolicyConsts* consts, const float
 }
 
 int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob,
-                      const DDPolicyConsts* consts, int32_t mode, uint32_t t0, int32_t T, uint8_t* actions_tn, float* logp_tn, float* reward_tn, uint8_t* done_tn,
+                      const DDPolicyConsts* consts, int32_t mode, float temperature, uint32_t t0, int32_t T, uint8_t* actions_tn, float* logp_tn, float* reward_tn, uint8_t* done_tn,
                       float* obs_tn, float* probs_tn, float* shaped_tn, uint64_t* stats, int64_t n, void* stream)
 {
     if (!s || !p || !c || !blob || !consts) return DD_E_NULL;
     if (s->dtype != DD_F32) return DD_E_DTYPE;                 // the fused kernel is the fp32 throughput path
     if (mode != DD_ACTION_THRESHOLD && mode != DD_ACTION_SAMPLE) return DD_E_RANGE;
+    if (mode == DD_ACTION_SAMPLE && !(temperature > 0.0f)) return DD_E_RANGE;
     if (T < 0 || n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
     if (n > 0 && (!s->pos_vel || !s->att_fuel || !s->platform || !s->steps || !s->episode || !s->flags)) return DD_E_NULL;
     if ((reinterpret_cast<uintptr_t>(s->pos_vel) | reinterpret_cast<uintptr_t>(s->att_fuel) | reinterpret_cast<uintptr_t>(blob)) & 15u) return DD_E_ALIGN;
@@ -798,6 +805,7 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     pa.a.rand_drone = c->randomize_drone; pa.a.rand_platform = c->randomize_platform;
     pa.a.k = dd::make_consts<float>(*p);
     pa.blob = (const uint8_t*)blob; pa.mode = mode; pa.t0 = t0; pa.T = T;
+    pa.inv_temperature = mode == DD_ACTION_SAMPLE ? 1.0f / temperature : 1.0f;
     pa.actions_tn = actions_tn; pa.logp_tn = logp_tn; pa.reward_tn = reward_tn; pa.done_tn = done_tn;
     pa.obs_tn = obs_tn; pa.probs_tn = probs_tn; pa.obs_in = nullptr; pa.auto_reset = c->auto_reset;
     return dd::policy_launch(pa, *p, n, false, (cudaStream_t)stream);

@@ -124,12 +124,18 @@ def rollout_values(vblob: PolicyBlob, obs_tn: torch.Tensor, final_obs: torch.Ten
 
 
 def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool = True, t0: int = 0,
-                   want: str = "arld", out: Optional[Dict[str, torch.Tensor]] = None, stats: bool = True
-                   ) -> Dict[str, torch.Tensor]:
+                   want: str = "arld", out: Optional[Dict[str, torch.Tensor]] = None, stats: bool = True,
+                   temperature: float = 1.0) -> Dict[str, torch.Tensor]:
     """T fused steps on ``env`` (float32 envs only).  ``want`` picks the [T,N] buffers to fill:
     a=actions (uint8 DD_ACT bits), l=logp, r=reward, d=done flags, o=obs [T,N,15], p=probs [T,N,3],
     s=shaped (the notebook's client-side training reward, Actor_Critic_PPO.ipynb c7 + c16:L89-93).
+    ``temperature``: the evaluation sampling of the notebooks' ``evaluate_policy_simple`` (c18) -- actions drawn from
+    ``p**(1/t) / (p**(1/t) + (1-p)**(1/t))``; 0 means ``probs > 0.5`` (like ``sample=False``), 1 the policy itself.
     Returns the dict of buffers (allocated unless passed in ``out``)."""
+    if temperature < 0:
+        raise ValueError("temperature must be >= 0")
+    if temperature == 0:
+        sample, temperature = False, 1.0
     if env.dtype != torch.float32:
         raise ValueError("policy_rollout needs a float32 env")
     if env._needs_reset:
@@ -150,7 +156,7 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
     ptr = lambda k: bufs[k].data_ptr() if k in bufs else None
     nv.check(nv.lib().dd_policy_rollout(
         C.byref(env._state), C.byref(env.params), C.byref(env._cfg), blob.blob.data_ptr(), C.byref(blob.consts),
-        ACTION_SAMPLE if sample else ACTION_THRESHOLD, int(t0), int(T), ptr("actions"), ptr("logp"), ptr("reward"),
+        ACTION_SAMPLE if sample else ACTION_THRESHOLD, float(temperature), int(t0), int(T), ptr("actions"), ptr("logp"), ptr("reward"),
         ptr("done"), ptr("obs"), ptr("probs"), ptr("shaped"), env.stats_slots.data_ptr() if stats else None, n,
         env._stream()),
         "dd_policy_rollout")

@@ -311,6 +311,30 @@ def test_policy_forward_large_persistent(fixture):
         assert torch.equal(big[lo:lo + 1003], dd.policy_forward(blob, x[lo:lo + 1003].contiguous()))
 
 
+def test_temperature_sampling_follows_the_notebook_formula(fixture):
+    """evaluate_policy_simple (Actor_Critic_PPO.ipynb c18): adjusted = p**(1/t) / (p**(1/t) + (1-p)**(1/t)), actions
+    ~ Bernoulli(adjusted); t = 0 is probs > 0.5.  The recorded probabilities stay the policy's own."""
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    n, T = 4096, 40
+    kw = dict(seed=11, randomize_drone=True, randomize_platform=True, max_steps=100, auto_reset=True, dtype=torch.float32)
+    for temp in (0.3, 2.5):
+        e = dd.BatchedDroneEnv(n, device=DEV, **kw); e.reset()
+        out = dd.policy_rollout(e, blob, T, sample=True, want="ap", temperature=temp)
+        p = out["probs"].double()
+        adj = p ** (1 / temp) / (p ** (1 / temp) + (1 - p) ** (1 / temp))
+        bits = torch.stack([(out["actions"] >> j) & 1 for j in range(3)], -1).double()
+        freq, exp = bits.mean((0, 1)), adj.mean((0, 1))
+        sd_ = (adj * (1 - adj)).sum((0, 1)).sqrt() / (T * n)
+        assert ((freq - exp).abs() < 6 * sd_).all(), (temp, freq, exp)
+        assert ((freq - p.mean((0, 1))).abs() > 6 * sd_).any()         # ... and not the untempered distribution
+    e = dd.BatchedDroneEnv(n, device=DEV, **kw); e.reset()
+    out0 = dd.policy_rollout(e, blob, T, want="ap", temperature=0)
+    assert torch.equal(out0["actions"], sum(((out0["probs"][..., j] > 0.5).to(torch.uint8) << j) for j in range(3)))
+    with pytest.raises(ValueError):
+        dd.policy_rollout(e, blob, T, temperature=-1.0)
+
+
 def test_policy_argument_errors(fixture):
     d, sd = fixture
     blob = dd.PolicyBlob(sd, device=DEV)
