@@ -169,7 +169,9 @@ struct RArgs {
 // POLICY (the action source) is a template parameter and every launch-constant switch is read once before the
 // loop: the kernel is bound by issue slots (no memory traffic to hide behind), so each instruction of the
 // per-step path is throughput.
-template <typename R, bool OBS, bool DEF, int POLICY>
+// OUTS = false: no per-step [T][n] outputs (reward / done / shaped) -- the pure statistics rollout of the curriculum
+// sweep and the throughput bench -- compiles their address arithmetic and predicated stores away.
+template <typename R, bool OBS, bool DEF, int POLICY, bool OUTS>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ RArgs<R> ra)
 {
     __shared__ __align__(128) R s_obs[OBS ? kBlock * kMaxObsStride : 1];
@@ -202,11 +204,11 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
             rb0 = __funnelshift_r(rb0, rb1, 3); rb1 = __funnelshift_r(rb1, rb2, 3); rb2 >>= 3;
         }
     }
-    const bool out_rew = ra.reward_tn != nullptr, out_done = ra.done_tn != nullptr, do_stats = a.stats != nullptr,
-               auto_reset = ra.auto_reset != 0;
+    const bool out_rew = OUTS && ra.reward_tn != nullptr, out_done = OUTS && ra.done_tn != nullptr,
+               do_stats = a.stats != nullptr, auto_reset = ra.auto_reset != 0;
     const int32_t max_steps = a.max_steps;
     // N2 (shaped training reward): normalised distance of the current state and of the one before it
-    const bool shaping = ra.shaped_tn != nullptr;
+    const bool shaping = OUTS && ra.shaped_tn != nullptr;
     R dprev = nan_of<R>(), dcur = (R)0;
     if (live && shaping) {
         R s_, d_;
@@ -472,13 +474,16 @@ static int rollout_impl(const DDState* s, const DDParams* p, const DDEnvConfig* 
     if (n == 0 || T == 0) return 0;
     const bool pdl = (c->launch_flags & DD_LAUNCH_PDL) != 0, def = params_are_default(*p);
     const int g = grid_for(n, kBlock);
-#define DD_ROLL(OBS_, DEF_)                                                                                        \
-    (policy == DD_POLICY_TRACE    ? launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_TRACE>, g, kBlock, st, pdl, ra)    \
-     : policy == DD_POLICY_RANDOM ? launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_RANDOM>, g, kBlock, st, pdl, ra)   \
-                                  : launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_BANGBANG>, g, kBlock, st, pdl, ra))
+    const bool outs = reward_tn || done_tn || shaped_tn;
+#define DD_ROLL2(OBS_, DEF_, OUTS_)                                                                                          \
+    (policy == DD_POLICY_TRACE    ? launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_TRACE, OUTS_>, g, kBlock, st, pdl, ra)    \
+     : policy == DD_POLICY_RANDOM ? launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_RANDOM, OUTS_>, g, kBlock, st, pdl, ra)   \
+                                  : launch(rollout_kernel<R, OBS_, DEF_, DD_POLICY_BANGBANG, OUTS_>, g, kBlock, st, pdl, ra))
+#define DD_ROLL(OBS_, DEF_) (outs ? DD_ROLL2(OBS_, DEF_, true) : DD_ROLL2(OBS_, DEF_, false))
     if (def) return obs_tn ? DD_ROLL(true, true) : DD_ROLL(false, true);
     return obs_tn ? DD_ROLL(true, false) : DD_ROLL(false, false);
 #undef DD_ROLL
+#undef DD_ROLL2
 }
 
 }  // namespace dd
