@@ -315,7 +315,9 @@ __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int
 // 512 rows: the "step" loop walks row blocks and the observation tile of the NEXT block is fetched by TMA
 // (cp.async.bulk -> mbarrier) while the current one goes through the layers.
 // HEAD: 3 = policy (probabilities); 1 = critic (FWD only): the two unused rows of the last Linear are not computed.
-template <bool DEF, int CH, bool FWD, int HEAD = 3>
+// EXTRA = false (rollout only): neither the shaped-reward nor the probabilities output is requested -- their code,
+// predicated stores and address arithmetic are compiled out (predicated-off instructions still cost issue slots).
+template <bool DEF, int CH, bool FWD, int HEAD = 3, bool EXTRA = true>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -399,12 +401,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint64_t gid = a.env_id_base + (uint64_t)i;
     float speed = 0.f, dist = 0.f;
     if (!forward_only) speed_dist(e, speed, dist);
-    const bool shaping = pa.shaped_tn != nullptr;
+    const bool shaping = EXTRA && pa.shaped_tn != nullptr;
     // The tile's observations of one step are 128 x 15 contiguous floats of obs_tn: full, 16-byte aligned tiles
     // are staged in shared memory (stride 15 words: conflict-free) and leave with one cp.async.bulk per step.
     // launch-constant switches, read from the argument block once
     const bool out_act = pa.actions_tn != nullptr, out_logp = pa.logp_tn != nullptr, out_rew = pa.reward_tn != nullptr,
-               out_done = pa.done_tn != nullptr, out_probs = pa.probs_tn != nullptr, do_stats = a.stats != nullptr,
+               out_done = pa.done_tn != nullptr, out_probs = EXTRA && pa.probs_tn != nullptr, do_stats = a.stats != nullptr,
                auto_reset = pa.auto_reset != 0, thresholded = pa.mode == DD_ACTION_THRESHOLD,
                tempered = pa.inv_temperature != 1.0f;
     const int32_t max_steps = a.max_steps;
@@ -721,7 +723,9 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
         grid = blocks < sms ? blocks : sms;                 // persistent: one CTA per SM walks the row blocks
         pa.T = (blocks + grid - 1) / grid;
     } else {
-        kern = def ? policy_rollout_kernel<true, kChunk, false> : policy_rollout_kernel<false, kChunk, false>;
+        const bool extra = pa.shaped_tn != nullptr || pa.probs_tn != nullptr;
+        kern = def ? (extra ? policy_rollout_kernel<true, kChunk, false, 3, true> : policy_rollout_kernel<true, kChunk, false, 3, false>)
+                   : (extra ? policy_rollout_kernel<false, kChunk, false, 3, true> : policy_rollout_kernel<false, kChunk, false, 3, false>);
     }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (err != cudaSuccess) return (int)err;
