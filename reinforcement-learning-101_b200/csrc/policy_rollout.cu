@@ -315,9 +315,11 @@ __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int
 // 512 rows: the "step" loop walks row blocks and the observation tile of the NEXT block is fetched by TMA
 // (cp.async.bulk -> mbarrier) while the current one goes through the layers.
 // HEAD: 3 = policy (probabilities); 1 = critic (FWD only): the two unused rows of the last Linear are not computed.
-// EXTRA = false (rollout only): neither the shaped-reward nor the probabilities output is requested -- their code,
-// predicated stores and address arithmetic are compiled out (predicated-off instructions still cost issue slots).
-template <bool DEF, int CH, bool FWD, int HEAD = 3, bool EXTRA = true>
+// FAST = true (rollout only): the PPO-collection configuration -- Bernoulli sampling at temperature 1, auto-reset,
+// statistics, and exactly the action / log-prob / reward / done / observation buffers (no shaped reward, no
+// probabilities) -- with every launch-constant switch a compile-time constant: predicated-off stores, their address
+// arithmetic and the selects between modes still cost issue slots, and this kernel is bound by them.
+template <bool DEF, int CH, bool FWD, int HEAD = 3, bool FAST = false>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -401,16 +403,17 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint64_t gid = a.env_id_base + (uint64_t)i;
     float speed = 0.f, dist = 0.f;
     if (!forward_only) speed_dist(e, speed, dist);
-    const bool shaping = EXTRA && pa.shaped_tn != nullptr;
+    const bool shaping = !FAST && pa.shaped_tn != nullptr;
     // The tile's observations of one step are 128 x 15 contiguous floats of obs_tn: full, 16-byte aligned tiles
     // are staged in shared memory (stride 15 words: conflict-free) and leave with one cp.async.bulk per step.
     // launch-constant switches, read from the argument block once
-    const bool out_act = pa.actions_tn != nullptr, out_logp = pa.logp_tn != nullptr, out_rew = pa.reward_tn != nullptr,
-               out_done = pa.done_tn != nullptr, out_probs = EXTRA && pa.probs_tn != nullptr, do_stats = a.stats != nullptr,
-               auto_reset = pa.auto_reset != 0, thresholded = pa.mode == DD_ACTION_THRESHOLD,
-               tempered = pa.inv_temperature != 1.0f;
+    const bool out_act = FAST || pa.actions_tn != nullptr, out_logp = FAST || pa.logp_tn != nullptr,
+               out_rew = FAST || pa.reward_tn != nullptr, out_done = FAST || pa.done_tn != nullptr,
+               out_probs = !FAST && pa.probs_tn != nullptr, do_stats = FAST || a.stats != nullptr,
+               auto_reset = FAST || pa.auto_reset != 0, thresholded = !FAST && pa.mode == DD_ACTION_THRESHOLD,
+               tempered = !FAST && pa.inv_temperature != 1.0f;
     const int32_t max_steps = a.max_steps;
-    const bool obs_out = !forward_only && pa.obs_tn != nullptr;
+    const bool obs_out = !forward_only && (FAST || pa.obs_tn != nullptr);
     const bool obs_bulk = obs_out && tile0 + kTile <= a.n && (a.n & 3u) == 0u &&
                           (reinterpret_cast<uintptr_t>(pa.obs_tn) & 15u) == 0u;
     float dprev = nan_of<float>(), dcur = dist * k.inv_width;
@@ -723,9 +726,10 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
         grid = blocks < sms ? blocks : sms;                 // persistent: one CTA per SM walks the row blocks
         pa.T = (blocks + grid - 1) / grid;
     } else {
-        const bool extra = pa.shaped_tn != nullptr || pa.probs_tn != nullptr;
-        kern = def ? (extra ? policy_rollout_kernel<true, kChunk, false, 3, true> : policy_rollout_kernel<true, kChunk, false, 3, false>)
-                   : (extra ? policy_rollout_kernel<false, kChunk, false, 3, true> : policy_rollout_kernel<false, kChunk, false, 3, false>);
+        const bool fast = pa.mode == DD_ACTION_SAMPLE && pa.inv_temperature == 1.0f && pa.auto_reset && pa.a.stats &&
+                          pa.actions_tn && pa.logp_tn && pa.reward_tn && pa.done_tn && pa.obs_tn && !pa.shaped_tn && !pa.probs_tn;
+        kern = def ? (fast ? policy_rollout_kernel<true, kChunk, false, 3, true> : policy_rollout_kernel<true, kChunk, false, 3, false>)
+                   : (fast ? policy_rollout_kernel<false, kChunk, false, 3, true> : policy_rollout_kernel<false, kChunk, false, 3, false>);
     }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (err != cudaSuccess) return (int)err;
