@@ -182,6 +182,15 @@ def test_rollout_env_half_is_exact_and_buffers_are_consistent(fixture):
     assert torch.equal(dd.policy_rollout(a2, blob, T, sample=True, t0=3, want="a")["actions"], out["actions"])
     a3 = dd.BatchedDroneEnv(n, device=DEV, **kw); a3.reset()
     assert not torch.equal(dd.policy_rollout(a3, blob, T, sample=True, t0=4, want="a")["actions"], out["actions"])
+    # (6) the PPO-collection fast-path instantiation (exactly want="arldo", sampling, auto-reset, statistics: every switch
+    # compile-time) computes what the generic one (taken above because of the probabilities output) computes
+    a4 = dd.BatchedDroneEnv(n, device=DEV, **kw); a4.reset()
+    fast = dd.policy_rollout(a4, blob, T, sample=True, t0=3, want="arldo")
+    for key in ("actions", "reward", "logp", "done", "obs"):
+        assert torch.equal(fast[key], out[key]), key
+    assert a4.stats() == a.stats()
+    for k_, v in a.get_state().items():
+        assert _eq(v, a4.get_state()[k_]), k_
 
 
 def test_threshold_rollout_lands_with_the_trained_policy(fixture):
