@@ -43,7 +43,7 @@
 // statistics under the first, the Philox draws under the second, sin / cos of the pre-update angle under the
 // third.  Measured:
 // T(k tiles per SM) = 0.70 ms + k x 0.21 ms per 250 steps -- the slope is the issue slots of one more warp
-// per scheduler (~1,770 instructions per env-step), the intercept the latency of one tile's serial chain;
+// per scheduler (~1,700 instructions per env-step), the intercept the latency of one tile's serial chain;
 // the tensor pipe is ~40 % busy.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
