@@ -31,7 +31,7 @@ def collect_episodes(env: BatchedDroneEnv, max_steps: int, policy: str = "random
     if env.auto_reset:
         raise ValueError("collect_episodes needs an env built with auto_reset=False (one episode per env)")
     env.max_steps = int(max_steps)
-    env.reset()
+    env.reset(want_obs=False)                      # the rollout launch reads the state, not the observation buffer
     env.reset_stats()
     if policy == "network":
         if blob is None:

@@ -159,9 +159,21 @@ class BatchedDroneEnv:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ---- DroneGame.reset ------------------------------------------------------------------------
-    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def reset(self, mask: Optional[torch.Tensor] = None, want_obs: bool = True) -> Optional[torch.Tensor]:
         """``DroneGame.reset()`` (game_engine.py:59-93) for all envs, or those with ``mask[i]`` set.
-        Returns the observation tensor ``[N, obs_stride]`` (rows of unmasked envs are refreshed too)."""
+        Returns the observation tensor ``[N, obs_stride]`` (rows of unmasked envs are refreshed too);
+        ``want_obs=False`` skips writing it (half of the reset's memory traffic) and returns None -- for callers
+        that go straight into a rollout launch."""
+        if not want_obs:
+            m = None
+            if mask is not None:
+                m = mask.to(device=self.device).ne(0).to(torch.uint8).contiguous()
+                if m.shape != (self.num_envs,):
+                    raise ValueError("mask must have shape [num_envs]")
+            nv.check(self._lib.dd_reset(C.byref(self._state), C.byref(self.params), C.byref(self._cfg), _ptr(m),
+                                        None, self.obs_stride, self.num_envs, self._stream()), "dd_reset")
+            self._needs_reset = False
+            return None
         m = None
         if mask is not None:
             m = mask.to(device=self.device).ne(0).to(torch.uint8).contiguous()
