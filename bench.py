@@ -243,6 +243,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus = dd.bind_to_gpu_numa(local) if ws > 1 and not args.no_numa_bind else None   # host buffers next to the GPU
     K, W, S, n = args.steps, args.warmup, args.shards, args.envs
     peak_gbs, peak_src = _peaks()
 
@@ -527,7 +528,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e2e / Ke,
                     "api": f"BatchedDroneEnv.step_host(chunks={args.e2e_chunks}) (pinned host actions in; obs, reward, flags out)",
                     "pcie_gbs": (h2d + d2h) / (ms_e2e / Ke * 1e-3) / 1e9,
-                    "bound": "PCIe: 65 B per env-step device->host (obs 60 + reward 4 + flags 1)"},
+                    "bound": "PCIe: 65 B per env-step device->host (obs 60 + reward 4 + flags 1)",
+                    "rank0_cpu_affinity": None if cpus is None else f"{len(cpus)} CPUs local to the GPU (NVML)"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "episode_stats_shard0": stats,
@@ -567,6 +569,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=1, help="step_host pipelines the step over this many env slices (D2H of slice k overlaps H2D + kernel of slice k+1)")
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs (N > 1)")
     ap.add_argument("--no-socket", action="store_true", help="skip the socket-shim context measurement")
     ap.add_argument("--no-policy", action="store_true", help="skip the fused policy rollout variant (K5)")
     ap.add_argument("--no-curriculum", action="store_true", help="skip the curriculum sweep variant (cfg 5)")

@@ -45,6 +45,25 @@ def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
     return rank, local, ws
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin the calling thread to the CPUs NVML reports as local to this GPU (same NUMA node / PCIe root), so that
+    pinned host buffers allocated afterwards are first-touched next to the GPU and the host side of host<->device
+    copies does not cross sockets.  Matters for host-buffer stepping at several ranks per box; returns the CPU list, or
+    None when NVML / affinity control is unavailable (never raises)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block [env_id_base, env_id_base + n_local) of global env ids owned by ``rank``.
     The first ``total % world`` ranks get one extra env."""
