@@ -180,10 +180,23 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------
+BYTES_GYM_F64 = 282       # the float64 (exact-parity) instantiation: read 84 + 1, write 68 + reward 8 + flags 1 + obs 120
+FLOP_STEP = 2 * (15 * 128 + 128 * 128 + 128 * 64 + 64 * 3)              # 53,376 per env-step (policy)
+FLOP_ROW_CRITIC = 2 * (15 * 128 + 128 * 128 + 128 * 64 + 64 * 1)        # critic head is 64 -> 1
+
+
+def _peaks_all():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = json.load(open(p)) if os.path.exists(p) else {}
+    return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "hbm_src": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in d else "fallback (B200_PROFILING.md 6.65 TB/s)",
+            "bf16_sustained": float(d.get("bf16_tflops_sustained", 1400.0)), "bf16_burst": float(d.get("bf16_tflops", 1600.0)),
+            "bf16_src": "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernels timed inside a long loop)" if "bf16_tflops_sustained" in d else "fallback (B200_PROFILING.md)"}
+
+
 def _ncu_traffic(n: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of step_kernel<float,AUTO,OBS> from the committed
-    ncu capture (profiles/r01_traffic_steady.json; ncu cannot run inside the bench).  Only valid for the
-    launch size it was captured at."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of step_kernel<float,AUTO,OBS> from the COMMITTED
+    ncu capture (profiles/r01_traffic_steady.json; ncu cannot run inside the bench) -- a constant read from that file,
+    not measured in this run, and only valid for the launch size it was captured at."""
     path = os.path.join(ROOT, "profiles", "r01_traffic_steady.json")
     try:
         with open(path) as f:
@@ -191,7 +204,7 @@ def _ncu_traffic(n: int):
         k = d["kernels"]["void step_kernel<float, 1, 1, 1, 256>(KArgs<T1>)"]
         if d["algorithmic_bytes_per_launch"]["step_kernel<float,AUTO,OBS>"] != BYTES_GYM * n:
             return None, f"profiles/r01_traffic_steady.json was captured at another launch size than {n} envs"
-        return k["dram_bytes_per_launch"], "profiles/r01_traffic_steady.json (ncu, steady state, --cache-control none)"
+        return k["dram_bytes_per_launch"], "constant from the committed capture profiles/r01_traffic_steady.json (ncu, steady state, --cache-control none); not measured in this run"
     except (OSError, KeyError, ValueError):
         return None, "no ncu capture committed"
 
@@ -233,6 +246,7 @@ def socket_shim_rate(dev, games: int = 6, seconds: float = 2.0):
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     dd = importlib.import_module("reinforcement-learning-101_b200")
@@ -244,8 +258,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cpus = dd.bind_to_gpu_numa(local) if ws > 1 and not args.no_numa_bind else None   # host buffers next to the GPU
-    K, W, S, n = args.steps, args.warmup, args.shards, args.envs
-    peak_gbs, peak_src = _peaks()
+    K, W, S, n = args.steps, max(args.warmup, 3), args.shards, args.envs
+    PK = _peaks_all()
+    peak_gbs = PK["hbm_gbs"]
+    launches = 0
 
     def barrier():
         if ws > 1:
@@ -259,113 +275,126 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- SHARDS independent 1M-env shards per GPU; global env ids are unique over the whole job ----
-    envs = [dd.BatchedDroneEnv(n, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
-                               max_steps=MAX_STEPS, auto_reset=True, dtype=torch.float32,
-                               env_id_base=(rank * S + s) * n, launch_flags=args.launch_flags) for s in range(S)]
-    for e in envs:
-        e.reset()
-    TRACE = 64                                            # steps of pre-generated actions per shard
-    traces = [e.random_actions(TRACE) for e in envs]
-    launches = 0
-
-    def eager_steps(k0: int, k: int, want_obs: bool, only_chain=None):
-        for j in range(k0, k0 + k):
-            s = j % S
-            if only_chain is not None and s % C_ != only_chain:
-                continue
-            envs[s].step_raw(traces[s][(j // S) % TRACE], want_obs=want_obs)
-
-    def timed(fn_warm, fn_run):
+    def timed(fn_warm, fn_run, sampler=None):
+        """warm-up, barrier + sync, CUDA events around fn_run on the current stream, barrier + sync, max over ranks.
+        `sampler` polls NVML from a thread exactly while the timed region runs."""
         fn_warm()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.start()
         e0.record()
         fn_run()
         e1.record()
+        torch.cuda.synchronize(dev)
+        if sampler is not None:
+            sampler.stop()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    # CUDA graph of G consecutive steps (a whole number of shard rotations) removes the host launch cost
-    G = S * max(1, min(TRACE, 96 // S))
+    # ---- the product path: dd.ShardedDroneEnv (S independent 1M-env shards, parallel chains, CUDA graphs) ----
+    def make_sharded(dtype, shards):
+        env = dd.ShardedDroneEnv(shards, n, device=dev, chains=args.chains, trace_len=args.trace_len,
+                                 use_graphs=not args.eager, env_id_base=rank * shards * n, launch_flags=args.launch_flags,
+                                 seed=0, randomize_drone=True, randomize_platform=True, max_steps=MAX_STEPS,
+                                 auto_reset=True, dtype=dtype)
+        env.reset()
+        env.random_trace()
+        return env
 
-    # Shards are independent environments, so their step launches need no mutual ordering: the graph
-    # has C_ parallel chains (shard s on chain s % C_).  Each shard's own steps stay stream-ordered;
-    # kernels of different chains overlap, which hides the fill / drain of one ~15 us launch behind
-    # the next (a single chain leaves ~3 us of pipeline drain between dependent launches).
-    C_ = max(1, min(args.chains, S))
-    chain_streams = [torch.cuda.Stream(dev) for _ in range(C_)]
+    def time_steps(env, want_obs, sampler=None, est_us=25.0):
+        """R repeats of the K-step block, R sized so that the timed region is >= --min-time-ms; every block runs
+        through env.run(K): graph replays whatever K is.  Returns (ms_total, R)."""
+        period = env.S * env.L
+        R = max(1, int(math.ceil(args.min_time_ms * 1e3 / (K * est_us))))
+        rehearse = max(R, period // math.gcd(K, period))        # visits every (offset, length) piece of the schedule
 
-    def make_graph(want_obs: bool):
-        g = torch.cuda.CUDAGraph()
-        side = chain_streams[0]
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            eager_steps(0, S, want_obs)                   # warm the capture stream
-            with torch.cuda.graph(g, stream=side):
-                for c in range(1, C_):                    # fork
-                    chain_streams[c].wait_stream(side)
-                for c in range(C_):
-                    with torch.cuda.stream(chain_streams[c]):
-                        eager_steps(0, G, want_obs, only_chain=c)
-                for c in range(1, C_):                    # join
-                    side.wait_stream(chain_streams[c])
-        torch.cuda.current_stream(dev).wait_stream(side)
-        return g
+        def blocks(r):
+            for _ in range(r):
+                env.run(K, want_obs=want_obs)
+        blocks(-(-W // K))                                      # the W warm-up steps
+        blocks(rehearse)                                        # all graphs captured before the clock starts
+        g0 = env.graphs_cached
+        ms = timed(lambda: None, lambda: blocks(R), sampler)
+        if max_over_ranks(float(env.graphs_cached != g0)) > 0:  # a capture happened inside the timed region (any rank): redo
+            ms = timed(lambda: None, lambda: blocks(R), sampler)
+        return ms, R
 
-    def run_steps(g, k: int, want_obs: bool):
-        q, r = divmod(k, G)
-        for _ in range(q):
-            g.replay()
-        eager_steps(0, r, want_obs)
+    sampler = ClockSampler(local, period_s=0.004)
+    env = make_sharded(torch.float32, S)
+    ms_gym, R_gym = time_steps(env, True, sampler)
+    launches += K * R_gym
+    ms_so, R_so = time_steps(env, False, None, est_us=15.0)
+    launches += K * R_so
+    launch_mode = (f"eager: one dd_step_planned call per step on {env.C} chain stream(s)" if args.eager else
+                   f"CUDA graphs (product path ShardedDroneEnv.run): the K-step block is cut at the {env.S * env.L}-launch schedule "
+                   f"period and each piece replays a cached graph; {env.C} parallel chain(s) over independent shards; "
+                   f"{env.graphs_cached} graphs cached, {env.graph_replays} replays, {env.eager_launches} eager launches")
+    launch_mode += f"; launch_flags={args.launch_flags:#x}"
 
-    sampler = ClockSampler(local)
-    results = {}
-    for name, want_obs in (("gym_step", True), ("step_only", False)):
-        g = make_graph(want_obs)
-        if name == "gym_step":
-            sampler.start()
-        ms = timed(lambda: run_steps(g, max(W, 3), want_obs), lambda: run_steps(g, K, want_obs))
-        if name == "gym_step":
-            sampler.stop()
-        launches += K
-        results[name] = ms
-        del g
-    # if the timed region was too short for NVML to see it, sample clocks over an untimed re-run
-    if sampler.h is not None and len(sampler.samples) < 5:
-        g = make_graph(True)
-        sampler.start()
-        t_end = time.perf_counter() + 0.5
-        while time.perf_counter() < t_end:
-            run_steps(g, G * 8, True)
-            torch.cuda.synchronize(dev)
-        sampler.stop()
-        del g
+    # host cost of one eager step through the public API (BatchedDroneEnv.step_raw -> dd_step_planned), GPU idle-free:
+    # time the Python loop alone for a small env so the GPU never back-pressures the queue
+    tiny = dd.BatchedDroneEnv(256, device=dev, seed=0, randomize_drone=True, randomize_platform=True, max_steps=MAX_STEPS,
+                              auto_reset=True, dtype=torch.float32)
+    tiny.reset()
+    tact = tiny.random_actions(1)[0]
+    for _ in range(200):
+        tiny.step_raw(tact)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        tiny.step_raw(tact)
+    host_us = (time.perf_counter() - t0) / 2000 * 1e6
+    torch.cuda.synchronize(dev)
+    launches += 2200
+    # ... and the eager product path on the full-size shards: what a caller that cannot use graphs gets
+    def eager_steps(k):
+        for j in range(k):
+            env.shards[j % S].step_raw(env.trace[(j // S) % env.L, j % S])
+    Ke = max(K, 240)
+    ms_eager = timed(lambda: eager_steps(S), lambda: eager_steps(Ke))
+    launches += Ke
+
+    # ---- the exact (float64) instantiation on the same workload: north_star's flag rule is met by this one ----
+    f64 = None
+    if not args.no_f64:
+        S64 = max(2, min(S, 4))
+        env64 = make_sharded(torch.float64, S64)
+        ms64, R64 = time_steps(env64, True, None, est_us=60.0)
+        launches += K * R64
+        a64 = n * BYTES_GYM_F64 / (ms64 * 1e-3 / (K * R64)) / 1e9
+        f64 = {"value": n * K * R64 * ws / (ms64 * 1e-3), "ms_per_step": ms64 / (K * R64), "dtype": "f64",
+               "algorithmic_bytes_per_env_step": BYTES_GYM_F64, "achieved_gbs": a64, "frac": a64 / peak_gbs,
+               "shards_per_gpu": S64, "repeats": R64, "timed_region_ms": ms64,
+               "what": "step_kernel<double,AUTO,OBS>: state, observations and rewards in float64, flags / counters bit-exact "
+                       "against the oracle (tests/test_gpu_parity.py); FP64 pipe bound on B200, not HBM bound"}
+        del env64
+        torch.cuda.empty_cache()
 
     # ---- T-steps-per-launch rollout kernel (state in registers; Philox actions in-kernel) ----
     T_ROLL = 50
     reps = max(1, K // T_ROLL // S) * S
+    shards = env.shards
 
     def run_rollouts(k):
         for j in range(k):
-            envs[j % S].rollout(T_ROLL, "random", t0=(j // S) * T_ROLL)
+            shards[j % S].rollout(T_ROLL, "random")
     ms_roll = timed(lambda: run_rollouts(S), lambda: run_rollouts(reps))
     launches += reps
 
     def run_rollouts_bb(k):                                 # cfg 3 (ii): fixed policy main = vy > 1.5, computed in-kernel
         for j in range(k):
-            envs[j % S].rollout(T_ROLL, "bangbang", t0=(j // S) * T_ROLL)
+            shards[j % S].rollout(T_ROLL, "bangbang")
     ms_roll_bb = timed(lambda: run_rollouts_bb(S), lambda: run_rollouts_bb(reps))
     launches += reps
 
     # ---- K5: fused policy rollout, BASELINE configs[3]: 65,536 envs x 250 steps, policy MLP in-kernel ----
-    k5 = None
+    k5, others = None, {}
     fix = os.path.join(ROOT, "tests", "golden", "policy_v1.npz")
     cfix_path = os.path.join(ROOT, "tests", "golden", "critic_v1.npz")
     if not args.no_policy and not (os.path.exists(fix) and os.path.exists(cfix_path)):
         k5 = {"skipped": "checkpoint fixtures tests/golden/policy_v1.npz / critic_v1.npz not found"}   # same on every rank
     elif not args.no_policy:
-        import numpy as np
         d = np.load(fix)
         sd = {kk: torch.from_numpy(d[kk]) for kk in d.files if kk.startswith("network")}
         blob = dd.PolicyBlob(sd, device=dev)
@@ -374,20 +403,24 @@ def run_ours(args):
                                   max_steps=MAX_STEPS, auto_reset=True, dtype=torch.float32, env_id_base=rank * NP)
         penv.reset()
         pbuf = dd.policy_rollout(penv, blob, TP, sample=True, want="arldo")      # allocates the rollout buffers
-        reps_p = max(2, min(10, K // 1000))
+        reps_p = 40                                          # ~50 ms per timed region
 
         def run_policy(kk):
-            for j in range(kk):
-                dd.policy_rollout(penv, blob, TP, sample=True, t0=j * TP, want="arldo", out=pbuf)
-        ms_pol = timed(lambda: run_policy(1), lambda: run_policy(reps_p))
-        launches += reps_p
-        FLOP_STEP = 2 * (15 * 128 + 128 * 128 + 128 * 64 + 64 * 3)              # 53,376
+            for _ in range(kk):
+                dd.policy_rollout(penv, blob, TP, sample=True, want="arldo", out=pbuf)      # t0: the env's running counter
+        ms_pol = timed(lambda: run_policy(2), lambda: run_policy(reps_p))
+        launches += reps_p + 2
         steps_s = NP * TP * reps_p * ws / (ms_pol * 1e-3)
-        k5 = {"value": steps_s, "envs_per_gpu": NP, "steps_per_launch": TP, "ms_per_launch": ms_pol / reps_p,
-              "mlp_tflops": steps_s / ws * FLOP_STEP / 1e12, "flop_per_env_step": FLOP_STEP,
+        tf = steps_s / ws * FLOP_STEP / 1e12
+        k5 = {"value": steps_s, "envs_per_gpu": NP, "steps_per_launch": TP, "ms_per_launch": ms_pol / reps_p, "launches_timed": reps_p,
+              "mlp_tflops": tf, "flop_per_env_step": FLOP_STEP, "frac_of_sustained_bf16": tf / PK["bf16_sustained"],
               "buffers": "obs[T,N,15] f32, action u8, logp f32, reward f32, done u8 (70 B/env-step)",
-              "policy": "drone_policy_v1 (27,651 params), Bernoulli sampling, bf16 tcgen05 MMA / fp32 accumulate",
+              "policy": "drone_policy_v1 (27,651 params), Bernoulli sampling, 16-bit tcgen05 MMA operands / fp32 accumulate",
+              "operands": getattr(blob, "operand_dtype", "bf16"),
               "stats": penv.stats(reduce=ws > 1)}
+        others["fused_policy_rollout_K5"] = {"bound": "tensor", "achieved": tf, "peak": PK["bf16_sustained"], "unit": "TFLOP/s",
+                                             "frac": tf / PK["bf16_sustained"], "frac_of_burst": tf / PK["bf16_burst"],
+                                             "ms_per_launch": ms_pol / reps_p, "algorithmic": f"{FLOP_STEP} FLOP x {NP} envs x {TP} steps per launch"}
         # 65,536 envs are 512 tiles of 128 = 128 CTAs: 20 of the 148 SMs idle.  One tile set per SM for reference.
         NF = 148 * 512
         fenv = dd.BatchedDroneEnv(NF, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
@@ -396,10 +429,10 @@ def run_ours(args):
         fbuf = dd.policy_rollout(fenv, blob, TP, sample=True, want="arldo")
 
         def run_policy_full(kk):
-            for j in range(kk):
-                dd.policy_rollout(fenv, blob, TP, sample=True, t0=j * TP, want="arldo", out=fbuf)
+            for _ in range(kk):
+                dd.policy_rollout(fenv, blob, TP, sample=True, want="arldo", out=fbuf)
         ms_full = timed(lambda: run_policy_full(1), lambda: run_policy_full(reps_p))
-        launches += reps_p
+        launches += reps_p + 1
         k5["all_148_sms"] = {"envs_per_gpu": NF, "ms_per_launch": ms_full / reps_p,
                              "value": NF * TP * reps_p * ws / (ms_full * 1e-3),
                              "mlp_tflops": NF * TP * reps_p / (ms_full * 1e-3) * FLOP_STEP / 1e12}
@@ -420,37 +453,80 @@ def run_ours(args):
                 dd.gae(pbuf["reward"], vals, dones, out=adv)
                 dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
         ms_tail = timed(lambda: run_ppo_tail(1), lambda: run_ppo_tail(reps_p))
-        launches += 5 * reps_p
+        launches += 5 * (reps_p + 1)
+        # each kernel of the tail alone, against its own roofline.  Working sets: critic 983 MB of observations, GAE 213 MB
+        # (> the 126 MB L2); moments / normalise rotate over four / two distinct 65 MB buffers so that no launch finds its
+        # input in L2.
+        ne = NP * TP
+        rot = [pbuf["reward"], pbuf["logp"], adv, nadv]
+        nrm_out = [torch.empty_like(adv), torch.empty_like(adv)]
+        mom = torch.zeros(3, dtype=torch.float64, device=dev)
+        mom1 = dd.advantage_moments(adv)
+
+        def t_values(kk):
+            for _ in range(kk):
+                dd.value_forward(vblob, pbuf["obs"], out=vals[:TP])
+        def t_gae(kk):
+            for _ in range(kk):
+                dd.gae(pbuf["reward"], vals, dones, out=adv)
+        def t_mom(kk):
+            for j in range(kk):
+                dd.advantage_moments(rot[j % 4], out=mom)
+        def t_nrm(kk):
+            lib = dd.native.lib()
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for j in range(kk):
+                lib.dd_normalize(rot[j % 2].data_ptr(), nrm_out[j % 2].data_ptr(), mom1.data_ptr(), 1e-8, ne, st)
+        rp = 4 * reps_p
+        ms_v = timed(lambda: t_values(1), lambda: t_values(reps_p)) / reps_p
+        ms_g = timed(lambda: t_gae(2), lambda: t_gae(rp)) / rp
+        ms_m = timed(lambda: t_mom(4), lambda: t_mom(rp)) / rp
+        ms_n = timed(lambda: t_nrm(2), lambda: t_nrm(rp)) / rp
+        launches += reps_p + 3 * rp + 9
+        vtf = ne * FLOP_ROW_CRITIC / (ms_v * 1e-3) / 1e12
+        others["critic_value_forward"] = {"bound": "tensor", "achieved": vtf, "peak": PK["bf16_sustained"], "unit": "TFLOP/s",
+                                          "frac": vtf / PK["bf16_sustained"], "ms_per_launch": ms_v, "rows": ne}
+        for name, ms_, bytes_el, what in (
+                ("gae_kernel", ms_g, 13.0 + 4.0 / TP, "read reward 4 + value 4 + done 1, write advantage 4 B per element (+ the bootstrap row)"),
+                ("moments_kernel", ms_m, 4.0, "one read of the advantage buffer"),
+                ("normalize_kernel", ms_n, 8.0, "read 4 + write 4 B per element")):
+            ach = ne * bytes_el / (ms_ * 1e-3) / 1e9
+            others[name] = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                            "ms_per_launch": ms_, "elements": ne, "algorithmic_bytes_per_element": bytes_el, "what": what}
+        del rot, nrm_out
         # the same through HOST-side inputs / outputs, as one PPO iteration sees it: policy + critic weights come from
         # host state_dicts (packed and uploaded every iteration, like after an optimiser step), the rollout buffers
         # stay in HBM for the learner, the episode statistics and advantage moments go back to the host
         sd_host = {kk: v.clone() for kk, v in sd.items()}
         sdc_host = {kk: torch.from_numpy(cfix[kk]) for kk in cfix.files if kk.startswith("network")}
         t_it = []
-        for it in range(3 + reps_p):
+        n_it = 3 + min(reps_p, 10)
+        for it in range(n_it):
             barrier()
             t0 = time.perf_counter()
             b_it = dd.PolicyBlob(sd_host, device=dev)
             vb_it = dd.ValueBlob(sdc_host, device=dev)
             penv.reset_stats()
-            dd.policy_rollout(penv, b_it, TP, sample=True, t0=(100 + it) * TP, want="arldo", out=pbuf)
+            dd.policy_rollout(penv, b_it, TP, sample=True, want="arldo", out=pbuf)
             dd.rollout_values(vb_it, pbuf["obs"], penv.observe())
             dd.gae(pbuf["reward"], vals, dones, out=adv)
             dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
             st_it = penv.stats(reduce=ws > 1)                  # device -> host: synchronises
             t_it.append(time.perf_counter() - t0)
         launches += 9 * len(t_it)
-        it_s = max_over_ranks(sum(t_it[3:]) / reps_p * 1e3) * 1e-3
+        it_s = max_over_ranks(sum(t_it[3:]) / (n_it - 3) * 1e3) * 1e-3
         k5["ppo_iteration_e2e"] = {"what": "host state_dicts -> pack + upload (policy, critic) -> fused rollout -> critic values -> GAE -> "
                                            "advantage normalisation -> episode statistics back on the host; wall clock per iteration",
                                    "ms": it_s * 1e3, "env_steps_per_s": NP * TP * ws / it_s,
                                    "landing_rate": st_it["landing_rate"]}
         k5["ppo_data_path"] = {"what": "critic values [T+1,N] (tcgen05, persistent forward) + GAE + advantage normalisation on the rollout buffers",
                                "ms": ms_tail / reps_p, "samples_per_s": NP * TP * reps_p * ws / (ms_tail * 1e-3),
-                               "rollout_plus_tail_ms": (ms_pol + ms_tail) / reps_p}
+                               "rollout_plus_tail_ms": (ms_pol + ms_tail) / reps_p,
+                               "kernels_ms": {"value_forward": ms_v, "gae": ms_g, "moments": ms_m, "normalize": ms_n}}
 
     # ---- BASELINE configs[4]: curriculum sweep 75 -> 250, 2M envs per GPU, stats all-reduced over ranks ----
     cur = None
+    mgc = None
     if not args.no_curriculum:
         NC = args.curriculum_envs
         cenv = dd.BatchedDroneEnv(NC, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
@@ -467,56 +543,85 @@ def run_ours(args):
                "env_steps_per_s": sum(s_["env_steps"] for s_ in stages) / (ms_cur * 1e-3),
                "policy": "bang-bang (main = vy > 1.5), one episode per env per stage, freeze after done",
                "stages": [{k_: s_[k_] for k_ in ("max_steps", "success_rate", "avg_reward", "avg_steps")} for s_ in stages]}
+        # ---- N > 1: is the all-reduced result the sum of what every shard computes?  (SURVEY.md 8d cfg 5: "check
+        # against single-GPU recomputation"; Actor_Critic_PPO.ipynb c21:L94-95,L105,L169 is what the numbers stand for) ----
+        if ws > 1:
+            mgc = multi_gpu_check(dd, dist, cenv, caps[2], rank, ws, NC, dev)
+            launches += 8
         del cenv
 
     # ---- e2e: HOST buffers in, HOST buffers out, every step ----
-    io = [envs[s].make_host_io() for s in range(min(S, 2))]
-    host_trace = traces[0][:TRACE].cpu().pin_memory()
-    Ke = max(3, min(K, args.e2e_steps))
-
-    def run_e2e(k):
-        for j in range(k):
-            b = io[j % len(io)]
-            b["actions"].copy_(host_trace[j % TRACE])     # host-side: the caller's actions of this step
-            envs[j % S].step_host(b, chunks=args.e2e_chunks)
-    t0 = None
-
-    def run_e2e_timed():
-        run_e2e(Ke)
-    ms_e2e = timed(lambda: run_e2e(3), run_e2e_timed)
-    launches += Ke * max(1, args.e2e_chunks)
+    io = [shards[s].make_host_io() for s in range(min(S, 2))]
+    host_trace = env.trace[:, 0].cpu().pin_memory()         # [L, N]: the caller's actions of shard 0, on the host
+    Ke2 = max(3, min(K * 4, args.e2e_steps))
+    e2e_modes = {}
+    for mode in ("copy", "zero_copy"):
+        def run_e2e(k):
+            for j in range(k):
+                b = io[j % len(io)]
+                b["actions"].copy_(host_trace[j % env.L])    # host-side: the caller's actions of this step
+                shards[j % S].step_host(b, mode=mode)
+        ms_e2e = timed(lambda: run_e2e(3), lambda: run_e2e(Ke2))
+        launches += Ke2 + 3
+        e2e_modes[mode] = ms_e2e / Ke2
     h2d = n * 1
-    d2h = n * (envs[0].obs_stride * 4 + 4 + 1)
+    d2h = n * (shards[0].obs_stride * 4 + 4 + 1)
+    # the ceiling of this box for the same bytes: plain cudaMemcpyAsync of the packed block into pinned memory, all
+    # ranks at once (profiles/pcie_ceiling.py is the standalone version)
+    blk_d, blk_h = shards[0]._out_block, io[0]["block"]
 
-    stats = None
-    for e in envs[:1]:
-        stats = e.stats(reduce=ws > 1)
+    def run_copy(k):
+        for _ in range(k):
+            blk_h.copy_(blk_d, non_blocking=True)
+    ms_ceil = timed(lambda: run_copy(3), lambda: run_copy(30)) / 30
+    ceil_gbs = blk_d.numel() / (ms_ceil * 1e-3) / 1e9
+    best_mode = min(e2e_modes, key=e2e_modes.get)
+    ms_e2e_step = e2e_modes[best_mode]
+
+    stats = env.stats(reduce=ws > 1)
 
     if rank == 0:
-        ms = results["gym_step"]
-        value = n * K * ws / (ms * 1e-3)
-        per_launch_s = ms * 1e-3 / K
+        steps_timed = K * R_gym
+        value = n * steps_timed * ws / (ms_gym * 1e-3)
+        per_launch_s = ms_gym * 1e-3 / steps_timed
         achieved = n * BYTES_GYM / per_launch_s / 1e9
         traffic, traffic_src = _ncu_traffic(n)
-        so_ms = results["step_only"]
-        so_achieved = n * BYTES_STEP_ONLY / (so_ms * 1e-3 / K) / 1e9
+        so_per = ms_so * 1e-3 / (K * R_so)
+        so_achieved = n * BYTES_STEP_ONLY / so_per / 1e9
+        eg_ach = n * BYTES_GYM / (ms_eager * 1e-3 / Ke) / 1e9
+        others["step_kernel_step_only"] = {"bound": "hbm", "achieved": so_achieved, "peak": peak_gbs, "unit": "GB/s",
+                                           "frac": so_achieved / peak_gbs, "algorithmic_bytes_per_env_step": BYTES_STEP_ONLY}
+        if f64 is not None:
+            others["step_kernel_f64"] = {"bound": "hbm", "achieved": f64["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+                                         "frac": f64["frac"], "algorithmic_bytes_per_env_step": BYTES_GYM_F64,
+                                         "note": "limited by the FP64 pipe of B200, reported against HBM for comparison"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": K, "warmup": W,
+            "ms_per_step": ms_gym / steps_timed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
+            "repeats": R_gym, "timed_region_ms": ms_gym, "steps_timed": steps_timed,
             "config": {"workload": WORKLOAD, "envs_per_gpu_per_step": n, "shards_per_gpu": S,
                        "l2": f"inputs larger than L2: steps rotate over {S} independent {n}-env shards "
                              f"({S} x ~{n * 116 >> 20} MiB state+outputs > 126 MB L2)",
-                       "launch": f"CUDA graph of {G} step launches, replayed, {C_} parallel chain(s) over independent shards; launch_flags={args.launch_flags:#x}", "parallelism": f"env-sharded x{ws}, no per-step comms"},
+                       "launch": launch_mode, "parallelism": f"env-sharded x{ws}, no per-step comms",
+                       "timing": f"the K = {K}-step block repeated {R_gym}x back to back inside one CUDA-event pair "
+                                 f"(>= {args.min_time_ms:.0f} ms); ms_per_step = timed_region_ms / (K x repeats); clocks sampled by NVML "
+                                 f"every 4 ms inside that region"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel<float,AUTO,OBS>", "achieved": achieved, "peak": peak_gbs,
                          "unit": "GB/s", "frac": achieved / peak_gbs, "frac_of_nominal_8000_gbs": achieved / 8000.0,
                          "traffic": traffic, "traffic_unit": "bytes per launch",
-                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_GYM * n, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n},
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_GYM * n, "peak_source": PK["hbm_src"],
+                         "algorithmic_bytes_per_env_step": BYTES_GYM, "env_steps_per_launch": n,
+                         "others": others, "others_tensor_peak_source": PK["bf16_src"]},
             "variants": {
-                "step_only": {"value": n * K * ws / (so_ms * 1e-3), "ms_per_step": so_ms / K,
+                "step_only": {"value": n * K * R_so * ws / (ms_so * 1e-3), "ms_per_step": so_per * 1e3,
                               "algorithmic_bytes_per_env_step": BYTES_STEP_ONLY, "achieved_gbs": so_achieved,
-                              "frac": so_achieved / peak_gbs},
+                              "frac": so_achieved / peak_gbs, "repeats": R_so, "timed_region_ms": ms_so},
+                "gym_step_f64": f64,
+                "gym_step_eager_api": {"value": n * Ke * ws / (ms_eager * 1e-3), "ms_per_step": ms_eager / Ke, "achieved_gbs": eg_ach,
+                                       "frac": eg_ach / peak_gbs, "steps": Ke, "host_us_per_step_raw_call": host_us,
+                                       "what": "BatchedDroneEnv.step_raw called from Python once per step (dd_step_planned), single chain, "
+                                               "no graph: the path of a caller with a policy in the loop"},
                 "rollout_T50_fixed_policy_bangbang": {"value": n * T_ROLL * reps * ws / (ms_roll_bb * 1e-3),
                                                       "ms_per_launch": ms_roll_bb / reps, "steps_per_launch": T_ROLL},
                 "rollout_T50_in_kernel_actions": {"value": n * T_ROLL * reps * ws / (ms_roll * 1e-3),
@@ -524,16 +629,21 @@ def run_ours(args):
                 "fused_policy_rollout": k5,
                 "curriculum_sweep": cur,
             },
-            "e2e": {"value": n * Ke * ws / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e2e / Ke,
-                    "api": f"BatchedDroneEnv.step_host(chunks={args.e2e_chunks}) (pinned host actions in; obs, reward, flags out)",
-                    "pcie_gbs": (h2d + d2h) / (ms_e2e / Ke * 1e-3) / 1e9,
+            "e2e": {"value": n * ws / (ms_e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke2, "ms_per_step": ms_e2e_step,
+                    "api": f"BatchedDroneEnv.step_host(mode='{best_mode}') (pinned host actions in; obs, reward, flags out in pinned host memory)",
+                    "modes_ms_per_step": e2e_modes,
+                    "pcie_gbs": (h2d + d2h) / (ms_e2e_step * 1e-3) / 1e9,
+                    "pcie_ceiling_gbs": ceil_gbs, "frac_of_pcie_ceiling": (d2h / (ms_e2e_step * 1e-3) / 1e9) / ceil_gbs,
+                    "pcie_ceiling_what": f"cudaMemcpyAsync device->pinned host of the same {blk_d.numel()} B block, {ws} rank(s) concurrently, max over ranks",
                     "bound": "PCIe: 65 B per env-step device->host (obs 60 + reward 4 + flags 1)",
                     "rank0_cpu_affinity": None if cpus is None else f"{len(cpus)} CPUs local to the GPU (NVML)"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "episode_stats_shard0": stats,
+            "episode_stats": stats,
         }
+        if mgc is not None:
+            line["multi_gpu_check"] = mgc
         if ws == 1 and not args.no_socket:
             try:
                 line["socket_shim"] = socket_shim_rate(dev)
@@ -556,6 +666,50 @@ def run_ours(args):
     return 0
 
 
+def multi_gpu_check(dd, dist, cenv, cap, rank, ws, NC, dev):
+    """On-hardware check of the two collectives (every rank computes it; returns the same dict everywhere).
+    (1) episode statistics: every rank plays one curriculum stage on its own env ids AND on its right neighbour's
+        (env_id_base = ((rank + 1) % ws) * NC -- trajectories are keyed by the global env id, so another GPU must get the
+        same 8 words); the per-rank words are all-gathered and the all-reduced block must equal their sum, and each
+        rank's neighbour recomputation must equal what the neighbour itself reported.
+    (2) advantage moments: normalize_advantages(reduce=True) on per-rank buffers must equal normalising the
+        concatenation of all ranks' buffers on one GPU."""
+    import torch
+    own = dd.collect_episodes(cenv, cap, policy="bangbang", reduce=False)
+    w_own = cenv.stats_tensor().clone()
+    w_red = dd.allreduce_stats(w_own.clone())
+    gathered = [torch.zeros_like(w_own) for _ in range(ws)]
+    dist.all_gather(gathered, w_own)
+    G = torch.stack(gathered)
+    nb = (rank + 1) % ws
+    nenv = dd.BatchedDroneEnv(NC, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                              auto_reset=False, dtype=torch.float32, env_id_base=nb * NC)
+    dd.collect_episodes(nenv, cap, policy="bangbang", reduce=False)
+    w_nb = nenv.stats_tensor().clone()
+    ok_sum = bool(torch.equal(G.sum(0), w_red))
+    ok_nb = bool(torch.equal(w_nb, G[nb]))
+    del nenv
+    # moments: a deterministic per-rank buffer (the shaped rewards of a short rollout would do; a hash is enough here)
+    m = 1 << 18
+    idx = torch.arange(m, device=dev, dtype=torch.float32)
+    x = torch.sin(idx * 0.37 + rank) * (3.0 + rank) + 0.1 * rank
+    y_red = dd.normalize_advantages(x, reduce=True)
+    xs = [torch.zeros_like(x) for _ in range(ws)]
+    dist.all_gather(xs, x)
+    y_all = dd.normalize_advantages(torch.cat(xs), reduce=False)
+    err = float((y_all[rank * m:(rank + 1) * m] - y_red).abs().max())
+    flags = torch.tensor([int(ok_sum), int(ok_nb), int(err < 1e-6)], device=dev, dtype=torch.int32)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    errt = torch.tensor([err], device=dev, dtype=torch.float64)
+    dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+    ok = bool(flags.min().item() == 1)
+    return {"status": "ok" if ok else "FAILED", "stats_allreduce_equals_sum_of_gathered": bool(flags[0].item()),
+            "neighbour_shard_recomputed_on_another_gpu_matches": bool(flags[1].item()),
+            "normalize_reduce_vs_single_buffer_max_abs_err": float(errt.item()),
+            "stage_max_steps": int(cap), "envs_per_rank": NC, "episodes_all_ranks": int(w_red[0].item()),
+            "landed_all_ranks": int(w_red[1].item()), "own_success_rate_rank0": own["success_rate"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
@@ -565,8 +719,11 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per shard (= per step launch)")
     ap.add_argument("--shards", type=int, default=6, help="independent shards per GPU that steps rotate over")
     ap.add_argument("--chains", type=int, default=2, help="parallel launch chains in the CUDA graph (shard s -> chain s %% chains)")
-    ap.add_argument("--e2e-steps", type=int, default=300)
-    ap.add_argument("--e2e-chunks", type=int, default=1, help="step_host pipelines the step over this many env slices (D2H of slice k overlaps H2D + kernel of slice k+1)")
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--trace-len", type=int, default=16, help="rows of the device action trace per shard (schedule period = shards x this)")
+    ap.add_argument("--min-time-ms", type=float, default=150.0, help="repeat the K-step block until the timed region is at least this long")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graphs: one Python -> C-ABI launch per step (A/B)")
+    ap.add_argument("--no-f64", action="store_true", help="skip the float64 (exact-parity) instantiation variant")
     ap.add_argument("--cpu-ticks", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs (N > 1)")

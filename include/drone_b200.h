@@ -6,7 +6,10 @@
  * host synchronisation (one documented exception: dd_policy_pack); work is enqueued
  * on the cudaStream_t passed in (as void*).
  * Return value: 0 = ok, < 0 = argument error (DD_E_*), > 0 = cudaError_t.
- * Safe to call concurrently on different streams / devices.
+ * Safe to call concurrently on different streams / devices.  The device a call runs on is the one
+ * that owns `stream` (a non-default stream) or, for the default stream, the one that owns the state
+ * / first buffer argument: the entry points switch to it for the duration of the call and restore
+ * the caller's current device, so an env on cuda:1 can be stepped while cuda:0 is current.
  *
  * The reference has no FFI: its "operator interface" for this path is the Python
  * class DroneGame (/root/reference/delivery_drone/game/game_engine.py).  Each entry
@@ -21,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DD_ABI_VERSION 3
+#define DD_ABI_VERSION 4
 
 /* ---- flag byte (per-step output and persistent state) ---------------------- */
 #define DD_DONE        0x01u   /* game_engine.py:53  self.done            */
@@ -116,7 +119,11 @@ typedef struct DDState {
     int32_t reserved;
     void *prev_dist;         /* R[n] or NULL: normalised distance_to_platform of the state observed before
                                 the previous step, NaN = none (prev_state of Actor_Critic_PPO.ipynb
-                                c16:L71-72,101-102).  Needed only when a shaped-reward output is requested. */
+                                c16:L71-72,101-102).  Needed only when a shaped-reward output is requested.
+                                Maintained by dd_rollout_shaped / dd_policy_rollout(shaped_tn) only: dd_step does
+                                NOT advance it (it only writes NaN on an auto-reset), so a caller that interleaves
+                                dd_step with the shaped rollouts must refill it with NaN first -- the shaped delta
+                                then restarts as at an episode start (BatchedDroneEnv does this). */
 } DDState;
 
 /* Per-call knobs shared by reset / step / rollout. */
@@ -151,8 +158,27 @@ int dd_step(const DDState *s, const DDParams *p, const DDEnvConfig *c, const uin
             void *obs, int32_t obs_stride, void *reward, uint8_t *done_flags, void *final_obs,
             uint64_t *stats, int64_t n, void *stream);
 
+/* ---- dd_step with the argument block built once -------------------------------------------------------
+ * A gym loop calls dd_step with the same buffers every step; only `actions` (and the stream) change.
+ * dd_step_plan validates the arguments once and stores the resolved launch (kernel, grid, argument block,
+ * owning device) in caller-owned memory; dd_step_planned then costs one driver launch -- no validation,
+ * no constant derivation, a 3-argument call for the binding.  Same kernel, same results as dd_step.
+ * The plan goes stale when a buffer moves or DDEnvConfig changes (max_steps ...): plan again. */
+#define DD_STEP_PLAN_BYTES 1024
+typedef struct DDStepPlan { uint64_t opaque[DD_STEP_PLAN_BYTES / 8]; } DDStepPlan;
+int dd_step_plan(const DDState *s, const DDParams *p, const DDEnvConfig *c,
+                 void *obs, int32_t obs_stride, void *reward, uint8_t *done_flags, void *final_obs,
+                 uint64_t *stats, int64_t n, DDStepPlan *plan);
+int dd_step_planned(const DDStepPlan *plan, const uint8_t *actions, void *stream);
+
 /* T steps in one launch, state held in registers (collect_episodes inner loop without a policy
- * network; Actor_Critic_PPO.ipynb c16:L42-108).  Optional [T][n] outputs. */
+ * network; Actor_Critic_PPO.ipynb c16:L42-108).  Optional [T][n] outputs.
+ *   obs_tn[t] is the observation AFTER step t (after the same-step reset, if any) -- the `next_state` a
+ *   gym loop gets back from step(), like dd_step's obs.  (dd_policy_rollout's obs_tn[t] is the observation
+ *   BEFORE step t, the network input: the two differ by one step.)
+ *   t0: DD_POLICY_RANDOM draws the action of call-local step t from Philox(seed, global env id, t0 + t), a pure
+ *   function of its arguments.  The CALLER owns t0: consecutive rollouts of the same envs must pass a running
+ *   offset (t0 += T), otherwise every rollout replays the same action noise.  BatchedDroneEnv keeps that counter. */
 int dd_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, int32_t policy,
                const uint8_t *actions_tn, uint32_t t0, int32_t T,
                void *reward_tn, uint8_t *done_tn, void *obs_tn, int32_t obs_stride,
@@ -256,7 +282,13 @@ int dd_value_forward(const void *blob, const DDPolicyConsts *consts, const float
  * (collect_episodes_ppo).  probs / logp outputs always describe the untempered policy. */
 /* T steps of {observe, policy, act, step} in one launch; DD_F32 state only.  Optional [T][n] outputs:
  * actions (DD_ACT_* bits), logp (sum of the 3 Bernoulli log-probs), reward, done flags, obs [T][n][15],
- * probs [T][n][3], shaped (the notebook's training reward; needs s->prev_dist). */
+ * probs [T][n][3], shaped (the notebook's training reward; needs s->prev_dist; c->shaping must be a DD_SHAPING_*
+ * value, else DD_E_RANGE).
+ *   obs_tn[t] is the observation BEFORE step t (what the policy saw; the `state` appended by
+ *   collect_episodes_ppo, c16:L66-80) -- values for dd_gae come from these rows plus the observation after the
+ *   last step as bootstrap row.
+ *   t0: the Bernoulli uniforms of call-local step t are Philox(seed, global env id, t0 + t, stream 2); as for
+ *   dd_rollout the caller owns t0 and must advance it by T between rollouts of the same envs. */
 int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c, const void *blob,
                       const DDPolicyConsts *consts, int32_t mode, float temperature, uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
                       uint8_t *done_tn, float *obs_tn, float *probs_tn, float *shaped_tn, uint64_t *stats, int64_t n,

@@ -14,7 +14,7 @@ from ._native import build_native
 from .distributed import (allreduce_moments, allreduce_stats, bind_to_gpu_numa, init_from_env, mean_std_from_moments,
                           shard_range, stats_dict)
 
-__all__ = ["native", "build_native", "BatchedDroneEnv", "StepInfo", "gae", "discounted_returns", "advantage_moments",
+__all__ = ["native", "build_native", "BatchedDroneEnv", "ShardedDroneEnv", "StepInfo", "gae", "discounted_returns", "advantage_moments",
            "normalize_advantages", "allreduce_stats", "allreduce_moments", "shard_range", "stats_dict",
            "mean_std_from_moments", "init_from_env", "bind_to_gpu_numa", "PolicyBlob", "ValueBlob", "policy_forward", "value_forward",
            "rollout_values", "policy_rollout",
@@ -27,6 +27,9 @@ def __getattr__(name):
     if name in ("BatchedDroneEnv", "StepInfo"):
         from . import env
         return getattr(env, name)
+    if name == "ShardedDroneEnv":
+        from . import sharded
+        return sharded.ShardedDroneEnv
     if name in ("gae", "discounted_returns", "advantage_moments", "normalize_advantages"):
         from . import ppo_ops
         return getattr(ppo_ops, name)
@@ -36,7 +39,7 @@ def __getattr__(name):
     if name in ("step_schedule", "collect_episodes", "curriculum_sweep"):
         from . import curriculum
         return getattr(curriculum, name)
-    if name in ("compat", "env", "ppo_ops", "policy", "curriculum"):
+    if name in ("compat", "env", "ppo_ops", "policy", "curriculum", "sharded"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -18,11 +18,16 @@ LIB_PATH = os.environ.get("DRONE_B200_LIB") or os.path.join(_HERE, "libdrone_b20
 SOURCES = ("drone_kernels.cu", "ppo_kernels.cu", "policy_rollout.cu")
 NVCC_FLAGS = (
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+    "--extended-lambda", "--expt-relaxed-constexpr", "--threads", "0", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
 )
+# The HOST twins of dd_reset / dd_step / dd_rollout (include/drone_b200_host.h): test infrastructure in its own
+# library, built here so that it travels with the tree, loaded only by tests/ (never by this package).
+HOST_TWIN_PATH = os.path.join(_HERE, "libdrone_b200_host.so")
+HOST_TWIN_SOURCE = "host_twin.cpp"
+HOST_TWIN_FLAGS = ("-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared")
 
 # ---- constants of include/drone_b200.h ------------------------------------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 DONE, LANDED, CRASHED, TRUNCATED = 0x01, 0x02, 0x04, 0x08
 CAUSE_MASK, CAUSE_GROUND, CAUSE_FUEL, CAUSE_OOB = 0x30, 0x10, 0x20, 0x30
 ACT_MAIN, ACT_LEFT, ACT_RIGHT, ACT_SKIP = 0x01, 0x02, 0x04, 0x80
@@ -67,6 +72,11 @@ class DDEnvConfig(C.Structure):
     ]
 
 
+class DDStepPlan(C.Structure):
+    """Caller-owned storage of a resolved dd_step launch (dd_step_plan / dd_step_planned)."""
+    _fields_ = [("opaque", C.c_uint64 * 128)]
+
+
 class DDPolicy(C.Structure):
     """Device pointers to the fp32 parameters of the 15-128-128-64-3 LayerNorm MLP."""
     _fields_ = [(k, C.c_void_p) for k in (
@@ -96,13 +106,28 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *srcs]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("DD_NVCC_EXTRA", "").split(), "-o", LIB_PATH + ".tmp", *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
+
+
+def build_host_twin(force: bool = False) -> str:
+    """g++ -ffp-contract=off csrc/host_twin.cpp -> libdrone_b200_host.so (the host instantiation of drone_core.cuh
+    that tests/ check against the golden vectors on a machine without a GPU)."""
+    src = os.path.join(CSRC, HOST_TWIN_SOURCE)
+    deps = [src, os.path.join(CSRC, "drone_core.cuh"), os.path.join(os.path.dirname(_HERE), "include", "drone_b200.h"),
+            os.path.join(os.path.dirname(_HERE), "include", "drone_b200_host.h")]
+    if not force and os.path.exists(HOST_TWIN_PATH) and all(
+            os.path.getmtime(HOST_TWIN_PATH) >= os.path.getmtime(d) for d in deps):
+        return HOST_TWIN_PATH
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    subprocess.check_call([cxx, *HOST_TWIN_FLAGS, "-o", HOST_TWIN_PATH + ".tmp", src])
+    os.replace(HOST_TWIN_PATH + ".tmp", HOST_TWIN_PATH)
+    return HOST_TWIN_PATH
 
 
 class NativeError(RuntimeError):
@@ -134,6 +159,10 @@ def lib():
     L.dd_reset.argtypes = [PS, PP, PC, vp, vp, i32, i64, vp]
     L.dd_step.restype = C.c_int
     L.dd_step.argtypes = [PS, PP, PC, vp, vp, i32, vp, vp, vp, vp, i64, vp]
+    L.dd_step_plan.restype = C.c_int
+    L.dd_step_plan.argtypes = [PS, PP, PC, vp, i32, vp, vp, vp, vp, i64, C.POINTER(DDStepPlan)]
+    L.dd_step_planned.restype = C.c_int
+    L.dd_step_planned.argtypes = [C.POINTER(DDStepPlan), vp, vp]
     L.dd_rollout.restype = C.c_int
     L.dd_rollout.argtypes = [PS, PP, PC, i32, vp, u32, i32, vp, vp, vp, i32, vp, i64, vp]
     L.dd_rollout_shaped.restype = C.c_int
@@ -183,7 +212,9 @@ def default_params() -> DDParams:
 
 
 EXPORTS = (
-    "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_rollout", "dd_rollout_shaped",
+    "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_step_plan", "dd_step_planned",
+    "dd_rollout", "dd_rollout_shaped",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
     "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env", "dd_discounted_returns",
 )
+HOST_TWIN_EXPORTS = ("dd_host_abi_version", "dd_reset_host", "dd_step_host", "dd_rollout_host")

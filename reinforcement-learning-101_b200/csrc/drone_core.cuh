@@ -167,8 +167,10 @@ template <> struct Arith<float> {
         // sin(pi * deg/180): exact range reduction, no radians rounding, <= 1 ulp each
         sincospif(deg * (1.0f / 180.0f), &s, &c);
 #else
-        const double rad = (double)deg * (3.14159265358979323846 / 180.0);
-        s = (float)sin(rad); c = (float)cos(rad);
+        // host twin: the same argument rounding as the device (deg / 180 in float), then sin / cos of pi * that in
+        // float64 rounded once -- within 1 ulp of sincospif's result
+        const double a = (double)(deg * (1.0f / 180.0f)) * 3.14159265358979323846;
+        s = (float)sin(a); c = (float)cos(a);
 #endif
     }
 };

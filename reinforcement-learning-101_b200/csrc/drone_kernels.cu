@@ -19,6 +19,7 @@
 #include <string.h>
 #include <utility>
 #include "drone_device.cuh"
+#include "host_guard.h"
 
 namespace dd {
 
@@ -412,17 +413,57 @@ static int reset_impl(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     if (obs) { if (int rc = check_stride(obs_stride)) return rc; a.obs_stride = obs_stride; }
     a.obs = (R*)obs;
     if (n == 0) return 0;
+    DeviceGuard g(st, s->pos_vel);
+    if (g.err != cudaSuccess) return (int)g.err;
     return launch(reset_kernel<R>, grid_for(n, kBlock), kBlock, st, (c->launch_flags & DD_LAUNCH_PDL) != 0, a, mask);
 }
 
+// The resolved launch of one dd_step call: what dd_step_plan stores in the caller's DDStepPlan.
+template <typename R>
+struct StepPlanT {
+    uint32_t magic;
+    int32_t dtype, device, grid, block, pdl;
+    void (*kern)(KArgs<R>);
+    KArgs<R> a;                                            // everything but `actions`
+};
+constexpr uint32_t kPlanMagic = 0x44445034u;               // "DDP4"
+static_assert(sizeof(StepPlanT<double>) <= DD_STEP_PLAN_BYTES && sizeof(StepPlanT<float>) <= DD_STEP_PLAN_BYTES,
+              "DD_STEP_PLAN_BYTES too small for the argument block");
+
 template <typename R, bool AUTO, bool OBS, bool DEF>
-static int step_launch(const KArgs<R>& a, int block, cudaStream_t st, bool pdl)
+static void (*step_kernel_of(int block))(KArgs<R>)
 {
     if constexpr (sizeof(R) == 4) {                        // CTA-size variants: float only (tuning knob)
-        if (block == 128) return launch(step_kernel<R, AUTO, OBS, DEF, 128>, grid_for(a.n, 128), 128, st, pdl, a);
-        if (block == 512) return launch(step_kernel<R, AUTO, OBS, DEF, 512>, grid_for(a.n, 512), 512, st, pdl, a);
+        if (block == 128) return step_kernel<R, AUTO, OBS, DEF, 128>;
+        if (block == 512) return step_kernel<R, AUTO, OBS, DEF, 512>;
     }
-    return launch(step_kernel<R, AUTO, OBS, DEF, 256>, grid_for(a.n, 256), 256, st, pdl, a);
+    return step_kernel<R, AUTO, OBS, DEF, 256>;
+}
+
+// Validate a dd_step call and resolve it to (kernel, grid, block, argument block).
+template <typename R>
+static int step_resolve(StepPlanT<R>& pl, const DDState* s, const DDParams* p, const DDEnvConfig* c,
+                        void* obs, int32_t obs_stride, void* reward, uint8_t* done_flags, void* final_obs,
+                        uint64_t* stats, int64_t n)
+{
+    KArgs<R>& a = pl.a;
+    if (int rc = fill_args(a, s, p, c, n)) return rc;
+    if (obs || final_obs) { if (int rc = check_stride(obs_stride)) return rc; a.obs_stride = obs_stride; }
+    a.obs = (R*)obs; a.reward = (R*)reward; a.final_obs = (R*)final_obs;
+    a.done_flags = done_flags; a.stats = (unsigned long long*)stats;
+    const bool au = c->auto_reset != 0, ob = obs != nullptr, def = params_are_default(*p);
+    const int bsel = (c->launch_flags >> 4) & 3;
+    int block = bsel == 1 ? 128 : (bsel == 2 ? 512 : 256);
+    if (sizeof(R) != 4) block = 256;
+    pl.magic = kPlanMagic; pl.dtype = sizeof(R) == 4 ? DD_F32 : DD_F64; pl.device = -1;
+    pl.block = block; pl.grid = grid_for(n, block); pl.pdl = (c->launch_flags & DD_LAUNCH_PDL) ? 1 : 0;
+#define DD_STEP(AU, OB, DF) step_kernel_of<R, AU, OB, DF>(block)
+    if (def) pl.kern = au ? (ob ? DD_STEP(true, true, true) : DD_STEP(true, false, true))
+                          : (ob ? DD_STEP(false, true, true) : DD_STEP(false, false, true));
+    else     pl.kern = au ? (ob ? DD_STEP(true, true, false) : DD_STEP(true, false, false))
+                          : (ob ? DD_STEP(false, true, false) : DD_STEP(false, false, false));
+#undef DD_STEP
+    return 0;
 }
 
 template <typename R>
@@ -430,28 +471,26 @@ static int step_impl(const DDState* s, const DDParams* p, const DDEnvConfig* c, 
                      void* obs, int32_t obs_stride, void* reward, uint8_t* done_flags, void* final_obs,
                      uint64_t* stats, int64_t n, cudaStream_t st)
 {
-    KArgs<R> a;
-    if (int rc = fill_args(a, s, p, c, n)) return rc;
+    StepPlanT<R> pl;
+    if (int rc = step_resolve(pl, s, p, c, obs, obs_stride, reward, done_flags, final_obs, stats, n)) return rc;
     if (!actions && n > 0) return DD_E_NULL;
-    if (obs || final_obs) { if (int rc = check_stride(obs_stride)) return rc; a.obs_stride = obs_stride; }
-    a.actions = actions; a.obs = (R*)obs; a.reward = (R*)reward; a.final_obs = (R*)final_obs;
-    a.done_flags = done_flags; a.stats = (unsigned long long*)stats;
     if (n == 0) return 0;
-    const bool au = c->auto_reset != 0, ob = obs != nullptr, def = params_are_default(*p);
-    const bool pdl = (c->launch_flags & DD_LAUNCH_PDL) != 0;
-    const int bsel = (c->launch_flags >> 4) & 3, block = bsel == 1 ? 128 : (bsel == 2 ? 512 : 256);
-#define DD_STEP(AU, OB, DF) step_launch<R, AU, OB, DF>(a, block, st, pdl)
-    if (def) {
-        if (au && ob) return DD_STEP(true, true, true);
-        if (au) return DD_STEP(true, false, true);
-        if (ob) return DD_STEP(false, true, true);
-        return DD_STEP(false, false, true);
-    }
-    if (au && ob) return DD_STEP(true, true, false);
-    if (au) return DD_STEP(true, false, false);
-    if (ob) return DD_STEP(false, true, false);
-    return DD_STEP(false, false, false);
-#undef DD_STEP
+    DeviceGuard g(st, s->pos_vel);
+    if (g.err != cudaSuccess) return (int)g.err;
+    pl.a.actions = actions;
+    return launch(pl.kern, pl.grid, pl.block, st, pl.pdl != 0, pl.a);
+}
+
+template <typename R>
+static int step_planned(const StepPlanT<R>& pl, const uint8_t* actions, cudaStream_t st)
+{
+    if (pl.a.n == 0) return 0;
+    if (!actions) return DD_E_NULL;
+    DeviceGuard g(pl.device);
+    if (g.err != cudaSuccess) return (int)g.err;
+    KArgs<R> a = pl.a;
+    a.actions = actions;
+    return launch(pl.kern, pl.grid, pl.block, st, pl.pdl != 0, a);
 }
 
 template <typename R>
@@ -472,6 +511,8 @@ static int rollout_impl(const DDState* s, const DDParams* p, const DDEnvConfig* 
     ra.shaped_tn = (R*)shaped_tn;
     ra.t0 = t0; ra.T = T; ra.policy = policy; ra.auto_reset = c->auto_reset;
     if (n == 0 || T == 0) return 0;
+    DeviceGuard guard(st, s->pos_vel);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     const bool pdl = (c->launch_flags & DD_LAUNCH_PDL) != 0, def = params_are_default(*p);
     const int g = grid_for(n, kBlock);
     const bool outs = reward_tn || done_tn || shaped_tn;
@@ -531,6 +572,39 @@ int dd_step(const DDState* s, const DDParams* p, const DDEnvConfig* c, const uin
     return DD_E_DTYPE;
 }
 
+int dd_step_plan(const DDState* s, const DDParams* p, const DDEnvConfig* c, void* obs, int32_t obs_stride,
+                 void* reward, uint8_t* done_flags, void* final_obs, uint64_t* stats, int64_t n, DDStepPlan* plan)
+{
+    if (!s || !plan) return DD_E_NULL;
+    if (s->dtype != DD_F32 && s->dtype != DD_F64) return DD_E_DTYPE;
+    memset(plan, 0, sizeof *plan);
+    int rc, *device;
+    if (s->dtype == DD_F32) {
+        auto* pl = reinterpret_cast<dd::StepPlanT<float>*>(plan);
+        rc = dd::step_resolve(*pl, s, p, c, obs, obs_stride, reward, done_flags, final_obs, stats, n);
+        device = &pl->device;
+    } else {
+        auto* pl = reinterpret_cast<dd::StepPlanT<double>*>(plan);
+        rc = dd::step_resolve(*pl, s, p, c, obs, obs_stride, reward, done_flags, final_obs, stats, n);
+        device = &pl->device;
+    }
+    if (rc) { memset(plan, 0, sizeof *plan); return rc; }
+    // the state buffers name the device the planned launches run on
+    const cudaError_t e = dd::owning_device(nullptr, n > 0 ? s->pos_vel : nullptr, device);
+    if (e != cudaSuccess) { memset(plan, 0, sizeof *plan); return (int)e; }
+    return 0;
+}
+
+int dd_step_planned(const DDStepPlan* plan, const uint8_t* actions, void* stream)
+{
+    if (!plan) return DD_E_NULL;
+    const auto* hdr = reinterpret_cast<const dd::StepPlanT<float>*>(plan);
+    if (hdr->magic != dd::kPlanMagic) return DD_E_RANGE;             // not (or no longer) a plan
+    if (hdr->dtype == DD_F32) return dd::step_planned(*hdr, actions, (cudaStream_t)stream);
+    if (hdr->dtype == DD_F64) return dd::step_planned(*reinterpret_cast<const dd::StepPlanT<double>*>(plan), actions, (cudaStream_t)stream);
+    return DD_E_DTYPE;
+}
+
 int dd_rollout_shaped(const DDState* s, const DDParams* p, const DDEnvConfig* c, int32_t policy,
                       const uint8_t* actions_tn, uint32_t t0, int32_t T, void* reward_tn, uint8_t* done_tn,
                       void* obs_tn, int32_t obs_stride, void* shaped_tn, uint64_t* stats, int64_t n, void* stream)
@@ -556,6 +630,8 @@ int dd_fill_random_actions(uint8_t* actions_tn, uint64_t seed, uint64_t env_id_b
     if (!actions_tn) return DD_E_NULL;
     if (n < 0 || T < 0) return DD_E_RANGE;
     if (n == 0 || T == 0) return 0;
+    dd::DeviceGuard g((cudaStream_t)stream, actions_tn);
+    if (g.err != cudaSuccess) return (int)g.err;
     dd::fill_random_actions_kernel<<<dd::grid_for(n, dd::kBlock), dd::kBlock, 0, (cudaStream_t)stream>>>(actions_tn, seed, env_id_base, t0, T, n);
     return (int)cudaGetLastError();
 }
@@ -567,6 +643,9 @@ int dd_gather_env(const DDState* s, const void* obs, int32_t obs_stride, const v
     if (!s->pos_vel || !s->att_fuel || !s->platform || !s->steps || !s->episode || !s->flags) return DD_E_NULL;
     if (i < 0 || i >= n) return DD_E_RANGE;
     if (obs && obs_stride != 15 && obs_stride != 16) return DD_E_RANGE;
+    if (s->dtype != DD_F32 && s->dtype != DD_F64) return DD_E_DTYPE;
+    dd::DeviceGuard g((cudaStream_t)stream, s->pos_vel);
+    if (g.err != cudaSuccess) return (int)g.err;
     if (s->dtype == DD_F32)
         dd::gather_env_kernel<float><<<1, 32, 0, (cudaStream_t)stream>>>(
             (const float*)s->pos_vel, (const float*)s->att_fuel, (const float*)s->platform, s->steps, s->episode, s->flags,
@@ -584,6 +663,8 @@ int dd_pack_actions(const uint8_t* actions3, uint8_t* packed, int64_t n, void* s
     if (!actions3 || !packed) return DD_E_NULL;
     if (n < 0) return DD_E_RANGE;
     if (n == 0) return 0;
+    dd::DeviceGuard g((cudaStream_t)stream, packed);
+    if (g.err != cudaSuccess) return (int)g.err;
     dd::pack_actions_kernel<<<dd::grid_for(n, dd::kBlock), dd::kBlock, 0, (cudaStream_t)stream>>>(actions3, packed, n);
     return (int)cudaGetLastError();
 }
@@ -594,6 +675,8 @@ int dd_stats_collapse(const uint64_t* stats, const int32_t* steps, const uint8_t
     if (!stats || !out) return DD_E_NULL;
     if (n < 0) return DD_E_RANGE;
     if (n > 0 && ((steps == nullptr) != (flags == nullptr))) return DD_E_NULL;
+    dd::DeviceGuard g((cudaStream_t)stream, stats);
+    if (g.err != cudaSuccess) return (int)g.err;
     dd::stats_collapse_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)stats, (unsigned long long*)out);
     if (steps && n > 0) {
         int g = dd::grid_for(n, dd::kBlock * 8);

@@ -50,6 +50,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "drone_device.cuh"
+#include "host_guard.h"
 
 namespace dd {
 
@@ -130,10 +131,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// A lost MMA / TMA completion must fault, never hang the GPU -- but the bound is WALL TIME (%globaltimer, 20 s),
+// not a poll count: under time-slicing, MPS preemption, ncu / compute-sanitizer replay or a debugger a healthy
+// kernel can spend any number of polls waiting.  The clock is read once per 2^16 polls, off the fast path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t_first = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();        // a lost MMA completion must fault, never hang the GPU
+        if ((++spins & 0xffffu) == 0u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_first == 0) t_first = now;
+            else if (now - t_first > 20000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -717,11 +727,12 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
     const bool def = pol_params_default(p);
     void (*kern)(PArgs);
     int grid = blocks;
+    DeviceGuard guard(st, pa.blob);                         // the device that owns the stream (or the blob)
+    if (guard.err != cudaSuccess) return (int)guard.err;
     if (forward) {
         kern = pa.head == 1 ? policy_rollout_kernel<true, kChunk, true, 1> : policy_rollout_kernel<true, kChunk, true, 3>;
-        int dev = 0, sms = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int sms = 0;
+        const cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, guard.dev);
         if (e != cudaSuccess) return (int)e;
         grid = blocks < sms ? blocks : sms;                 // persistent: one CTA per SM walks the row blocks
         pa.T = (blocks + grid - 1) / grid;
@@ -743,6 +754,8 @@ static int pack_common(const DDPolicy* p, int head, void* blob, DDPolicyConsts* 
     const float* const* q = reinterpret_cast<const float* const*>(p);
     for (int j = 0; j < 14; ++j) if (!q[j]) return DD_E_NULL;
     if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
+    DeviceGuard guard((cudaStream_t)stream, blob);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     policy_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*p, head, (uint8_t*)blob);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
@@ -802,6 +815,7 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     if ((reinterpret_cast<uintptr_t>(s->pos_vel) | reinterpret_cast<uintptr_t>(s->att_fuel) | reinterpret_cast<uintptr_t>(blob)) & 15u) return DD_E_ALIGN;
     if (reinterpret_cast<uintptr_t>(s->platform) & 7u) return DD_E_ALIGN;
     if (shaped_tn && !s->prev_dist && n > 0) return DD_E_NULL;
+    if (shaped_tn && c->shaping != DD_SHAPING_PPO && c->shaping != DD_SHAPING_PG) return DD_E_RANGE;
     if (n == 0 || T == 0) return 0;
     dd::PArgs pa{};
     pa.pc = *consts;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/drone_b200.h"
+#include "host_guard.h"
 
 namespace dd {
 
@@ -95,26 +96,33 @@ __global__ void __launch_bounds__(kRedBlock) normalize_kernel(const float* __res
 // it.  A thread-per-env scan has little parallelism at PPO sizes (65,536 envs = 443 threads per SM), so the
 // loop works in chunks of kGaeUnroll steps whose 3 x kGaeUnroll loads are all issued before the first is used:
 // the launch is bound by DRAM latency / kGaeUnroll instead of DRAM latency per step.
-constexpr int kGaeBlock = 64;
-constexpr int kGaeUnroll = 10;
+// Chunks are double-buffered in registers: the loads of chunk c+1 are issued BEFORE chunk c is scanned, so loads
+// stay in flight during the dependent arithmetic and the stores (round 1 issued them only after the scan of the
+// previous chunk: 4.4 TB/s; with the prefetch the kernel is bound by HBM, not by its latency).
+#ifndef DD_GAE_BLOCK
+#define DD_GAE_BLOCK 64
+#endif
+#ifndef DD_GAE_UNROLL
+#define DD_GAE_UNROLL 10
+#endif
+constexpr int kGaeBlock = DD_GAE_BLOCK;
+constexpr int kGaeUnroll = DD_GAE_UNROLL;
 
-__global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
-                                                        const uint8_t* __restrict__ done, float* __restrict__ adv,
-                                                        float* __restrict__ ret, float g, float gl, int32_t T, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
-    if (i >= n) return;
-    float gae = 0.0f;
-    float v_next = __ldg(val + (int64_t)T * n + i);
-    for (int32_t t1 = T; t1 > 0; t1 -= kGaeUnroll) {            // steps t1-1 ... max(t1-kGaeUnroll, 0)
-        float r[kGaeUnroll], v[kGaeUnroll];
-        uint8_t d[kGaeUnroll];
+struct GaeChunk {
+    float r[kGaeUnroll], v[kGaeUnroll];
+    uint8_t d[kGaeUnroll];
+    // steps t1-1 ... t1-kGaeUnroll (clamped at 0: the surplus loads of the last chunk re-read row 0)
+    __device__ __forceinline__ void load(const float* __restrict__ rew, const float* __restrict__ val,
+                                         const uint8_t* __restrict__ done, int32_t t1, int64_t n, int64_t i) {
 #pragma unroll
         for (int j = 0; j < kGaeUnroll; ++j) {
             const int32_t t = t1 - 1 - j;
             const int64_t o = (int64_t)(t >= 0 ? t : 0) * n + i;
             r[j] = __ldg(rew + o); v[j] = __ldg(val + o); d[j] = __ldg(done + o);
         }
+    }
+    __device__ __forceinline__ void scan(float* __restrict__ adv, float* __restrict__ ret, float g, float gl, int32_t t1,
+                                         int64_t n, int64_t i, float& gae, float& v_next) const {
 #pragma unroll
         for (int j = 0; j < kGaeUnroll; ++j) {
             const int32_t t = t1 - 1 - j;
@@ -128,6 +136,25 @@ __global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict_
                 v_next = v[j];
             }
         }
+    }
+};
+
+__global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                        const uint8_t* __restrict__ done, float* __restrict__ adv,
+                                                        float* __restrict__ ret, float g, float gl, int32_t T, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
+    if (i >= n) return;
+    float gae = 0.0f;
+    float v_next = __ldg(val + (int64_t)T * n + i);
+    GaeChunk a, b;
+    a.load(rew, val, done, T, n, i);
+    for (int32_t t1 = T; t1 > 0; t1 -= 2 * kGaeUnroll) {       // two chunks per trip: a = [t1-U, t1), b = [t1-2U, t1-U)
+        if (t1 - kGaeUnroll > 0) b.load(rew, val, done, t1 - kGaeUnroll, n, i);
+        a.scan(adv, ret, g, gl, t1, n, i, gae, v_next);
+        if (t1 - kGaeUnroll <= 0) break;
+        if (t1 - 2 * kGaeUnroll > 0) a.load(rew, val, done, t1 - 2 * kGaeUnroll, n, i);
+        b.scan(adv, ret, g, gl, t1 - kGaeUnroll, n, i, gae, v_next);
     }
 }
 
@@ -180,6 +207,8 @@ int dd_moments(const float* x, int64_t n, double* out, void* stream)
     if ((reinterpret_cast<uintptr_t>(x) & 3u) || (reinterpret_cast<uintptr_t>(out) & 7u)) return DD_E_ALIGN;
     if (n == 0) return 0;
     const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 4, dd::kSMs * 8);
+    dd::DeviceGuard guard((cudaStream_t)stream, x);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     dd::moments_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(x, n, out);
     return (int)cudaGetLastError();
 }
@@ -190,6 +219,8 @@ int dd_normalize(const float* x, float* y, const double* moments, double eps, in
     if (n < 0) return DD_E_RANGE;
     if (n == 0) return 0;
     const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 2, dd::kSMs * 8);
+    dd::DeviceGuard guard((cudaStream_t)stream, x);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     dd::normalize_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(x, y, moments, eps, n);
     return (int)cudaGetLastError();
 }
@@ -201,6 +232,8 @@ int dd_gae(const float* rewards_tn, const float* values_t1n, const uint8_t* done
     if (n < 0 || T < 0) return DD_E_RANGE;
     if (n == 0 || T == 0) return 0;
     const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
+    dd::DeviceGuard guard((cudaStream_t)stream, rewards_tn);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     dd::gae_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn,
                                                                        (float)gamma, (float)(gamma * lambda), T, n);
     return (int)cudaGetLastError();
@@ -213,6 +246,8 @@ int dd_discounted_returns(const float* rewards_tn, const uint8_t* dones_tn, floa
     if (n < 0 || T < 0) return DD_E_RANGE;
     if (n == 0 || T == 0) return 0;
     const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
+    dd::DeviceGuard guard((cudaStream_t)stream, rewards_tn);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     dd::returns_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, dones_tn, returns_tn, gamma, T, n);
     return (int)cudaGetLastError();
 }

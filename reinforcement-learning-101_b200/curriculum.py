@@ -24,9 +24,11 @@ def step_schedule(num_iterations: int, start: int = 300, end: int = 500, steepne
 
 
 def collect_episodes(env: BatchedDroneEnv, max_steps: int, policy: str = "random", blob=None, sample: bool = True,
-                     reduce: bool = True, t0: int = 0) -> Dict[str, float]:
+                     reduce: bool = True, t0: Optional[int] = None) -> Dict[str, float]:
     """One curriculum iteration: every env plays one episode of at most ``max_steps`` steps.
     ``policy``: 'random' / 'bangbang' (scripted, in-kernel) or 'network' with a ``PolicyBlob``.
+    ``t0``: offset of the in-kernel noise streams; ``None`` continues the env's running counter, so every stage /
+    iteration explores with fresh noise (include/drone_b200.h, t0 contract).
     Returns the (all-reduced) statistics dict: success_rate, avg_reward (engine return), avg_steps, ..."""
     if env.auto_reset:
         raise ValueError("collect_episodes needs an env built with auto_reset=False (one episode per env)")
@@ -50,6 +52,6 @@ def curriculum_sweep(env: BatchedDroneEnv, caps: Iterable[int], policy: str = "r
                      sample: bool = True, reduce: bool = True) -> List[Dict[str, float]]:
     """``collect_episodes`` for each cap in ``caps`` (e.g. ``step_schedule(8, 75, 250)``)."""
     out = []
-    for j, cap in enumerate(caps):
-        out.append(collect_episodes(env, int(cap), policy=policy, blob=blob, sample=sample, reduce=reduce, t0=0))
+    for cap in caps:        # t0=None: each stage continues the env's noise counter (stage j starts at sum(caps[:j]))
+        out.append(collect_episodes(env, int(cap), policy=policy, blob=blob, sample=sample, reduce=reduce))
     return out

@@ -34,6 +34,24 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _out_layout(n: int, stride: int, dtype: torch.dtype):
+    """Byte offsets of (obs, reward, step_flags, end) inside the packed per-step output block."""
+    isz = 4 if dtype == torch.float32 else 8
+    up = lambda b: -(-b // 256) * 256
+    o_rew = up(n * stride * isz)
+    o_flg = o_rew + up(n * isz)
+    return 0, o_rew, o_flg, max(o_flg + up(n), 256)
+
+
+def _carve(block: torch.Tensor, layout, n: int, stride: int, dtype: torch.dtype):
+    isz = 4 if dtype == torch.float32 else 8
+    o_obs, o_rew, o_flg, _ = layout
+    obs = block[o_obs:o_obs + n * stride * isz].view(dtype).view(n, stride)
+    reward = block[o_rew:o_rew + n * isz].view(dtype)
+    flags = block[o_flg:o_flg + n]
+    return obs, reward, flags
+
+
 class StepInfo(dict):
     """``info`` of a batched step.  ``flags`` (uint8 DD_* bits of THIS step) is always present;
     the derived boolean / counter views are materialised only when asked for."""
@@ -105,10 +123,11 @@ class BatchedDroneEnv:
         self.episode = torch.zeros(n, dtype=torch.int32, device=dev)   # uint32 bit pattern
         self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.prev_dist = torch.full((n,), float("nan"), dtype=dtype, device=dev)   # N2 shaping bookkeeping
-        # ---- per-step outputs ----
-        self.obs = torch.zeros(n, self.obs_stride, dtype=dtype, device=dev)
-        self.reward = torch.zeros(n, dtype=dtype, device=dev)
-        self.step_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # ---- per-step outputs: ONE block [obs | reward | step_flags] (256-byte aligned parts), so that the
+        #      host-buffer step moves them with a single device->host copy ----
+        self._out_layout = _out_layout(n, self.obs_stride, dtype)
+        self._out_block = torch.zeros(self._out_layout[-1], dtype=torch.uint8, device=dev)
+        self.obs, self.reward, self.step_flags = _carve(self._out_block, self._out_layout, n, self.obs_stride, dtype)
         self.final_obs = torch.zeros(n, self.obs_stride, dtype=dtype, device=dev) if want_final_obs else None
         self._packed = torch.zeros(n, dtype=torch.uint8, device=dev)
         # ---- episode statistics (K3) ----
@@ -123,6 +142,10 @@ class BatchedDroneEnv:
                                    int(launch_flags), nv.SHAPING_PG if shaping == "pg" else nv.SHAPING_PPO)
         self.shaping = shaping
         self._needs_reset = True
+        self._plans: Dict[tuple, "nv.DDStepPlan"] = {}       # resolved dd_step launches (dd_step_plan), by (want_obs, stats)
+        self._planned = self._lib.dd_step_planned
+        self._prev_dist_stale = False                      # dd_step does not advance prev_dist (include/drone_b200.h)
+        self.t_rollout = 0                                 # running step offset of the in-kernel RNG streams (t0 contract)
 
     # ---- configuration ------------------------------------------------------------------------
     @property
@@ -141,6 +164,7 @@ class BatchedDroneEnv:
     def max_steps(self, v: Optional[int]) -> None:
         """Curriculum knob (Actor_Critic_PPO.ipynb c19:L13-17): takes effect on the next step."""
         self._cfg.max_steps = int(v or 0)
+        self._plans.clear()
 
     @property
     def launch_flags(self) -> int:
@@ -150,6 +174,7 @@ class BatchedDroneEnv:
     def launch_flags(self, v: int) -> None:
         """``native.LAUNCH_PDL`` etc. (include/drone_b200.h DD_LAUNCH_*)."""
         self._cfg.launch_flags = int(v)
+        self._plans.clear()
 
     @property
     def auto_reset(self) -> bool:
@@ -225,12 +250,29 @@ class BatchedDroneEnv:
         env's own output buffers, overwritten by the next call."""
         if self._needs_reset:
             raise RuntimeError("call reset() before step()")
-        nv.check(self._lib.dd_step(
-            C.byref(self._state), C.byref(self.params), C.byref(self._cfg), packed.data_ptr(),
-            self.obs.data_ptr() if want_obs else None, self.obs_stride, self.reward.data_ptr(),
-            self.step_flags.data_ptr(), _ptr(self.final_obs), self.stats_slots.data_ptr() if stats else None,
-            self.num_envs, self._stream()), "dd_step")
+        plan = self._plans.get((want_obs, stats))
+        if plan is None:
+            plan = self._make_plan(want_obs, stats)
+        rc = self._planned(plan, packed.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            nv.check(rc, "dd_step_planned")
+        self._prev_dist_stale = True
         return self.obs, self.reward, self.step_flags
+
+    def _make_plan(self, want_obs: bool, stats: bool, obs=None, reward=None, flags=None, key=None):
+        """Resolve the dd_step launch for this env's buffers once (include/drone_b200.h dd_step_plan): a step is then
+        a 3-argument call.  ``obs`` / ``reward`` / ``flags`` override the destination addresses (e.g. device-mapped
+        pinned host memory for ``step_host(zero_copy=True)``)."""
+        plan = nv.DDStepPlan()
+        nv.check(self._lib.dd_step_plan(
+            C.byref(self._state), C.byref(self.params), C.byref(self._cfg),
+            (self.obs.data_ptr() if obs is None else obs) if want_obs else None, self.obs_stride,
+            self.reward.data_ptr() if reward is None else reward, self.step_flags.data_ptr() if flags is None else flags,
+            _ptr(self.final_obs), self.stats_slots.data_ptr() if stats else None, self.num_envs, C.byref(plan)), "dd_step_plan")
+        ref = C.byref(plan)
+        ref._plan = plan                                   # the byref object keeps the storage alive
+        self._plans[(want_obs, stats) if key is None else key] = ref
+        return ref
 
     def step(self, actions: torch.Tensor):
         """Gym-style: ``(obs [N,obs_stride], reward [N], done [N] bool, info)``.
@@ -245,12 +287,29 @@ class BatchedDroneEnv:
         return obs, reward, done, StepInfo(self, flags)
 
     # ---- T steps in one launch ---------------------------------------------------------------------
-    def rollout(self, T: int, policy: str = "random", actions: Optional[torch.Tensor] = None, t0: int = 0,
+    def _take_t0(self, t0: Optional[int], T: int) -> int:
+        """The t0 contract of include/drone_b200.h: the in-kernel RNG streams (random actions, Bernoulli uniforms) are
+        pure functions of (seed, env id, t0 + t).  ``t0=None`` uses this env's running counter and advances it by T, so
+        consecutive rollouts draw fresh noise; an explicit ``t0`` is used as given and leaves the counter alone."""
+        if t0 is not None:
+            return int(t0) & 0xffffffff
+        t = self.t_rollout
+        self.t_rollout = (t + int(T)) & 0xffffffff
+        return t
+
+    def _fresh_prev_dist(self) -> None:
+        """Before a shaped-reward rollout: if dd_step ran since the last one, prev_dist is stale -> 'no previous state'."""
+        if self._prev_dist_stale:
+            self.prev_dist.fill_(float("nan"))
+            self._prev_dist_stale = False
+
+    def rollout(self, T: int, policy: str = "random", actions: Optional[torch.Tensor] = None, t0: Optional[int] = None,
                 reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None,
                 obs_out: Optional[torch.Tensor] = None, shaped_out: Optional[torch.Tensor] = None, stats: bool = True):
         """T steps per launch with the env state in registers (one state round trip per launch).
         ``policy``: 'trace' (``actions`` uint8 ``[T,N]``), 'random' (Philox, p=0.5 per thruster;
-        examples/random_agent.py:27-31) or 'bangbang' (main = vy > 1.5).  Optional ``[T,N]`` outputs;
+        examples/random_agent.py:27-31; ``t0=None`` continues this env's noise stream, see ``_take_t0``) or
+        'bangbang' (main = vy > 1.5).  Optional ``[T,N]`` outputs (``obs_out[t]`` = observation AFTER step t);
         ``shaped_out`` receives the PPO notebook's client-side training reward (``calc_reward`` +
         time-out penalty, Actor_Critic_PPO.ipynb c7, c16:L89-93) computed in the same launch."""
         if self._needs_reset:
@@ -270,6 +329,9 @@ class BatchedDroneEnv:
                 raise ValueError("reward_out / obs_out / shaped_out must have the env dtype")
         if done_out is not None and done_out.dtype != torch.uint8:
             raise ValueError("done_out must be uint8")
+        if shaped_out is not None:
+            self._fresh_prev_dist()
+        t0 = self._take_t0(t0, T) if pol == nv.POLICY_RANDOM else int(t0 or 0)
         nv.check(self._lib.dd_rollout_shaped(
             C.byref(self._state), C.byref(self.params), C.byref(self._cfg), pol, _ptr(actions), int(t0), int(T),
             _ptr(reward_out), _ptr(done_out), _ptr(obs_out), self.obs_stride, _ptr(shaped_out),
@@ -352,65 +414,40 @@ class BatchedDroneEnv:
 
     # ---- host-buffer entry point (what a CPU-side caller such as the socket shim uses) -----------------
     def make_host_io(self):
-        """Pinned host buffers for ``step_host``."""
-        pin = dict(pin_memory=True)
-        return {
-            "actions": torch.zeros(self.num_envs, dtype=torch.uint8, **pin),
-            "obs": torch.zeros(self.num_envs, self.obs_stride, dtype=self.dtype, **pin),
-            "reward": torch.zeros(self.num_envs, dtype=self.dtype, **pin),
-            "flags": torch.zeros(self.num_envs, dtype=torch.uint8, **pin),
-        }
-
-    def step_host(self, io, chunks: int = 1) -> None:
-        """HOST in / HOST out step: copies ``io['actions']`` (pinned, packed uint8) to the device,
-        steps, copies obs / reward / flags back into ``io`` and waits for them.
-
-        ``chunks > 1`` pipelines the step over that many contiguous slices of the envs on two side streams, so
-        the device->host copy of slice k (65 B per env: what bounds this call, PCIe) overlaps the host->device
-        copy and the kernel of slice k+1.  Envs are independent and Philox is keyed by the global env id, so the
-        result is identical to the unchunked call.  Measured on B200 (1 M envs): the single-launch call already
-        moves 51.7 GB/s over PCIe and the per-slice host overhead outweighs the overlap (1.34 ms unchunked, 1.38 ms
-        with 4 slices, 1.51 ms with 8), so the default stays 1."""
-        if chunks <= 1 or self.num_envs < 2 * 256:
-            self._packed.copy_(io["actions"], non_blocking=True)
-            self.step_raw(self._packed)
-            io["obs"].copy_(self.obs, non_blocking=True)
-            io["reward"].copy_(self.reward, non_blocking=True)
-            io["flags"].copy_(self.step_flags, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            return
-        if self._needs_reset:
-            raise RuntimeError("call reset() before step()")
+        """Pinned host buffers for ``step_host``: ``actions`` (packed uint8 in) and ONE packed output block with the
+        same layout as the device's, of which ``obs`` / ``reward`` / ``flags`` are views."""
         n = self.num_envs
-        per = -(-n // chunks)
-        per = -(-per // 256) * 256                              # whole CTAs, 16-byte aligned observation slices
-        if getattr(self, "_side", None) is None:
-            self._side = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
-        main = torch.cuda.current_stream(self.device)
-        start = torch.cuda.Event()
-        start.record(main)
-        isz = self.pos_vel.element_size()
-        for c, lo in enumerate(range(0, n, per)):
-            hi = min(lo + per, n)
-            st = nv.DDState(self.pos_vel.data_ptr() + lo * 4 * isz, self.att_fuel.data_ptr() + lo * 4 * isz,
-                            self.platform.data_ptr() + lo * 2 * isz, self.steps.data_ptr() + lo * 4,
-                            self.episode.data_ptr() + lo * 4, self.flags.data_ptr() + lo, self._state.dtype, 0,
-                            self.prev_dist.data_ptr() + lo * isz)
-            cfg = nv.DDEnvConfig(self._cfg.seed, self._cfg.env_id_base + lo, self._cfg.max_steps, self._cfg.auto_reset,
-                                 self._cfg.randomize_drone, self._cfg.randomize_platform, self._cfg.launch_flags, 0)
-            sd = self._side[c % 2]
-            if c < 2:
-                sd.wait_event(start)
-            with torch.cuda.stream(sd):
-                self._packed[lo:hi].copy_(io["actions"][lo:hi], non_blocking=True)
-                nv.check(self._lib.dd_step(
-                    C.byref(st), C.byref(self.params), C.byref(cfg), self._packed.data_ptr() + lo,
-                    self.obs.data_ptr() + lo * self.obs_stride * isz, self.obs_stride, self.reward.data_ptr() + lo * isz,
-                    self.step_flags.data_ptr() + lo,
-                    None if self.final_obs is None else self.final_obs.data_ptr() + lo * self.obs_stride * isz,
-                    self.stats_slots.data_ptr(), hi - lo, sd.cuda_stream), "dd_step")
-                io["obs"][lo:hi].copy_(self.obs[lo:hi], non_blocking=True)
-                io["reward"][lo:hi].copy_(self.reward[lo:hi], non_blocking=True)
-                io["flags"][lo:hi].copy_(self.step_flags[lo:hi], non_blocking=True)
-        for sd in self._side:
-            sd.synchronize()
+        block = torch.zeros(self._out_layout[-1], dtype=torch.uint8, pin_memory=True)
+        obs, reward, flags = _carve(block, self._out_layout, n, self.obs_stride, self.dtype)
+        return {"actions": torch.zeros(n, dtype=torch.uint8, pin_memory=True), "block": block,
+                "obs": obs, "reward": reward, "flags": flags}
+
+    def step_host(self, io, mode: str = "copy") -> None:
+        """HOST in / HOST out step: copies ``io['actions']`` (pinned, packed uint8) to the device, steps, and
+        returns with obs / reward / flags of the step in ``io`` (pinned host memory).
+
+        ``mode='copy'``      the kernel writes its packed output block in HBM, ONE device->host copy brings it back
+                             (65 B per env-step: this copy is what bounds the call, PCIe);
+        ``mode='zero_copy'`` the kernel's obs / reward / flags destinations ARE the pinned host buffers (device-mapped
+                             under UVA): the observation tile of each CTA leaves the SM as one TMA bulk store straight
+                             over PCIe, there is no HBM round trip and no separate copy."""
+        stream = torch.cuda.current_stream(self.device)
+        self._packed.copy_(io["actions"], non_blocking=True)
+        if mode == "copy":
+            self.step_raw(self._packed)
+            io["block"].copy_(self._out_block, non_blocking=True)
+        elif mode == "zero_copy":
+            if self._needs_reset:
+                raise RuntimeError("call reset() before step()")
+            key = ("host", io["block"].data_ptr())
+            plan = self._plans.get(key)
+            if plan is None:
+                plan = self._make_plan(True, True, obs=io["obs"].data_ptr(), reward=io["reward"].data_ptr(),
+                                       flags=io["flags"].data_ptr(), key=key)
+            rc = self._planned(plan, self._packed.data_ptr(), stream.cuda_stream)
+            if rc:
+                nv.check(rc, "dd_step_planned")
+            self._prev_dist_stale = True
+        else:
+            raise ValueError("mode must be 'copy' or 'zero_copy'")
+        stream.synchronize()

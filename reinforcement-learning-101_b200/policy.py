@@ -123,12 +123,15 @@ def rollout_values(vblob: PolicyBlob, obs_tn: torch.Tensor, final_obs: torch.Ten
     return v
 
 
-def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool = True, t0: int = 0,
+def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool = True, t0: Optional[int] = None,
                    want: str = "arld", out: Optional[Dict[str, torch.Tensor]] = None, stats: bool = True,
                    temperature: float = 1.0) -> Dict[str, torch.Tensor]:
     """T fused steps on ``env`` (float32 envs only).  ``want`` picks the [T,N] buffers to fill:
     a=actions (uint8 DD_ACT bits), l=logp, r=reward, d=done flags, o=obs [T,N,15], p=probs [T,N,3],
     s=shaped (the notebook's client-side training reward, Actor_Critic_PPO.ipynb c7 + c16:L89-93).
+    ``t0``: offset of the Bernoulli noise stream (include/drone_b200.h: uniforms = Philox(seed, env id, t0 + t)); the
+    default ``None`` continues the env's own running counter (``env.t_rollout``, advanced by T), so that successive PPO
+    iterations explore with fresh noise.  ``obs[t]`` is the observation BEFORE step t (the network input).
     ``temperature``: the evaluation sampling of the notebooks' ``evaluate_policy_simple`` (c18) -- actions drawn from
     ``p**(1/t) / (p**(1/t) + (1-p)**(1/t))``; 0 means ``probs > 0.5`` (like ``sample=False``), 1 the policy itself.
     Returns the dict of buffers (allocated unless passed in ``out``)."""
@@ -154,6 +157,9 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
         if tuple(b.shape) != shape or b.dtype != dtype or not b.is_contiguous() or b.device != dev:
             raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {shape} on {dev}")
     ptr = lambda k: bufs[k].data_ptr() if k in bufs else None
+    if "shaped" in bufs:
+        env._fresh_prev_dist()
+    t0 = env._take_t0(t0, T)
     nv.check(nv.lib().dd_policy_rollout(
         C.byref(env._state), C.byref(env.params), C.byref(env._cfg), blob.blob.data_ptr(), C.byref(blob.consts),
         ACTION_SAMPLE if sample else ACTION_THRESHOLD, float(temperature), int(t0), int(T), ptr("actions"), ptr("logp"), ptr("reward"),
@@ -161,14 +167,3 @@ def policy_rollout(env: BatchedDroneEnv, blob: PolicyBlob, T: int, sample: bool 
         env._stream()),
         "dd_policy_rollout")
     return bufs
-
-
-def reference_policy(state_dict: Mapping[str, torch.Tensor], head: int = 3) -> torch.nn.Module:
-    """An eager fp32 torch module with the notebook's architecture (for tests / comparisons); head=1: the critic."""
-    net = torch.nn.Sequential(
-        torch.nn.Linear(15, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
-        torch.nn.Linear(128, 128), torch.nn.LayerNorm(128), torch.nn.ReLU(),
-        torch.nn.Linear(128, 64), torch.nn.LayerNorm(64), torch.nn.ReLU(),
-        *((torch.nn.Linear(64, 3), torch.nn.Sigmoid()) if head == 3 else (torch.nn.Linear(64, 1),)))
-    net.load_state_dict({k.replace("network.", ""): v for k, v in state_dict.items()})
-    return net

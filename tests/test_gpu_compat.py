@@ -111,25 +111,28 @@ def test_randomised_pool_spawns_in_reference_ranges():
     assert pool[3].episode == 2
 
 
-def test_step_host_chunked_pipeline_is_identical():
-    """step_host(chunks=k) pipelines H2D / kernel / D2H over env slices on side streams; envs are independent and
-    Philox is keyed by the global env id, so outputs, state and statistics equal the single-launch call."""
+def test_step_host_modes_are_identical():
+    """step_host: 'copy' (packed output block in HBM + one device->host copy) and 'zero_copy' (the kernel's obs /
+    reward / flags destinations are the pinned host buffers themselves) and plain device stepping give the same
+    outputs, state and statistics, at ragged sizes too (the TMA bulk store of a full tile and the fallback loop)."""
     import torch
-    n = 5000
-    kw = dict(device="cuda:0", seed=9, randomize_drone=True, randomize_platform=True, max_steps=25, auto_reset=True,
-              dtype=torch.float32, env_id_base=777)
-    a, b = dd.BatchedDroneEnv(n, **kw), dd.BatchedDroneEnv(n, **kw)
-    a.reset(); b.reset()
-    ioa, iob = a.make_host_io(), b.make_host_io()
-    g = torch.Generator().manual_seed(1)
-    for t in range(60):
-        act = torch.randint(0, 8, (n,), generator=g, dtype=torch.uint8)
-        ioa["actions"].copy_(act); iob["actions"].copy_(act)
-        a.step_host(ioa)
-        b.step_host(iob, chunks=(3 if t % 2 else 7))
-        for k_ in ("obs", "reward", "flags"):
-            assert torch.equal(ioa[k_], iob[k_]), (t, k_)
-    sa, sb = a.get_state(), b.get_state()
-    for k_ in sa:
-        assert torch.equal(torch.nan_to_num(sa[k_].double(), nan=-1.0), torch.nan_to_num(sb[k_].double(), nan=-1.0)), k_
-    assert a.stats() == b.stats()
+    for n in (5000, 4096, 257):
+        kw = dict(device="cuda:0", seed=9, randomize_drone=True, randomize_platform=True, max_steps=25, auto_reset=True,
+                  dtype=torch.float32, env_id_base=777)
+        a, b, c = dd.BatchedDroneEnv(n, **kw), dd.BatchedDroneEnv(n, **kw), dd.BatchedDroneEnv(n, **kw)
+        a.reset(); b.reset(); c.reset()
+        ioa, iob = a.make_host_io(), b.make_host_io()
+        g = torch.Generator().manual_seed(1)
+        for t in range(60):
+            act = torch.randint(0, 8, (n,), generator=g, dtype=torch.uint8)
+            ioa["actions"].copy_(act); iob["actions"].copy_(act)
+            a.step_host(ioa)
+            b.step_host(iob, mode="zero_copy")
+            obs, rew, fl = c.step_raw(act.to("cuda:0"))
+            for k_, ref in (("obs", obs), ("reward", rew), ("flags", fl)):
+                assert torch.equal(ioa[k_], iob[k_]), (n, t, k_)
+                assert torch.equal(ioa[k_], ref.cpu()), (n, t, k_)
+        sa, sb = a.get_state(), b.get_state()
+        for k_ in sa:
+            assert torch.equal(torch.nan_to_num(sa[k_].double(), nan=-1.0), torch.nan_to_num(sb[k_].double(), nan=-1.0)), k_
+        assert a.stats() == b.stats() == c.stats()

@@ -27,6 +27,8 @@ def _eq(a, b):
         a, b = torch.nan_to_num(a, nan=-12345.0), torch.nan_to_num(b, nan=-12345.0)
     return torch.equal(a, b)
 
+from torch_reference import reference_policy
+
 dd = importlib.import_module("reinforcement-learning-101_b200")
 pol = importlib.import_module("reinforcement-learning-101_b200.policy")
 nv = dd.native
@@ -101,7 +103,7 @@ def test_forward_matches_torch_on_the_reference_checkpoint(fixture):
     flips = (probs > 0.5) != (ref > 0.5)
     assert np.abs(d["logits"])[flips.numpy()].max(initial=0.0) < 0.05
     # the module-based constructor gives the same blob
-    blob2 = dd.PolicyBlob.from_module(pol.reference_policy(sd), device=DEV)
+    blob2 = dd.PolicyBlob.from_module(reference_policy(sd), device=DEV)
     assert torch.equal(blob.blob, blob2.blob)
 
 
@@ -140,7 +142,7 @@ def test_forward_degenerate_layernorm_gammas(fixture):
     probs = dd.policy_forward(blob, x.to(DEV)).cpu()
     assert torch.isfinite(probs).all()
     with torch.no_grad():
-        ref = pol.reference_policy(sd)(x)
+        ref = reference_policy(sd)(x)
     assert (probs - _emulate_bf16(sd, x)).abs().max().item() < 5e-3
     assert (probs - ref).abs().max().item() < 6e-2
 
@@ -295,7 +297,7 @@ def test_critic_value_forward_and_rollout_values(fixture, golden_dir):
     flat = dd.value_forward(vblob, out["obs"].view(-1, 15)[3:-5])            # unaligned start, ragged length
     assert torch.equal(flat, vals[:T].reshape(-1)[3:-5])
     with torch.no_grad():
-        eager = pol.reference_policy(sdc, head=1)(out["obs"].cpu().view(-1, 15)).squeeze(-1)
+        eager = reference_policy(sdc, head=1)(out["obs"].cpu().view(-1, 15)).squeeze(-1)
     assert (vals[:T].cpu().reshape(-1) - eager).abs().max().item() < 0.03 * scale
     # ... and straight into GAE + advantage normalisation (bit-exact against the notebook's loop: test_gpu_parity)
     adv = dd.normalize_advantages(dd.gae(out["reward"], vals, (out["done"] != 0).to(torch.uint8)), reduce=False)
