@@ -312,6 +312,7 @@ def run_ours(args):
         def blocks(r):
             for _ in range(r):
                 env.run(K, want_obs=want_obs)
+            env.join()                                          # the current stream (where the events are) waits for the chains
         blocks(-(-W // K))                                      # the W warm-up steps
         blocks(rehearse)                                        # all graphs captured before the clock starts
         g0 = env.graphs_cached
@@ -327,9 +328,10 @@ def run_ours(args):
     ms_so, R_so = time_steps(env, False, None, est_us=15.0)
     launches += K * R_so
     launch_mode = (f"eager: one dd_step_planned call per step on {env.C} chain stream(s)" if args.eager else
-                   f"CUDA graphs (product path ShardedDroneEnv.run): the K-step block is cut at the {env.S * env.L}-launch schedule "
-                   f"period and each piece replays a cached graph; {env.C} parallel chain(s) over independent shards; "
-                   f"{env.graphs_cached} graphs cached, {env.graph_replays} replays, {env.eager_launches} eager launches")
+                   f"CUDA graphs (product path ShardedDroneEnv.run): each K-step block is one piece of the {env.S * env.L}-launch "
+                   f"schedule and replays one cached graph per chain; {env.C} parallel chain(s) over independent shards, joined to "
+                   f"the timing stream once per timed region; {env.graphs_cached} pieces cached, {env.graph_replays} graph replays, "
+                   f"{env.eager_launches} eager launches")
     launch_mode += f"; launch_flags={args.launch_flags:#x}"
 
     # host cost of one eager step through the public API (BatchedDroneEnv.step_raw -> dd_step_planned), GPU idle-free:
@@ -347,13 +349,16 @@ def run_ours(args):
     host_us = (time.perf_counter() - t0) / 2000 * 1e6
     torch.cuda.synchronize(dev)
     launches += 2200
-    # ... and the eager product path on the full-size shards: what a caller that cannot use graphs gets
+    # ... and the eager product path on the full-size shards: what a caller that cannot use graphs gets -- the same
+    # schedule and chains, every launch a Python -> dd_step_planned call
     def eager_steps(k):
-        for j in range(k):
-            env.shards[j % S].step_raw(env.trace[(j // S) % env.L, j % S])
+        env.run(k)
+        env.join()
     Ke = max(K, 240)
+    env.use_graphs = False
     ms_eager = timed(lambda: eager_steps(S), lambda: eager_steps(Ke))
-    launches += Ke
+    env.use_graphs = not args.eager
+    launches += Ke + S
 
     # ---- the exact (float64) instantiation on the same workload: north_star's flag rule is met by this one ----
     f64 = None
@@ -374,6 +379,7 @@ def run_ours(args):
     # ---- T-steps-per-launch rollout kernel (state in registers; Philox actions in-kernel) ----
     T_ROLL = 50
     reps = max(1, K // T_ROLL // S) * S
+    env.join()
     shards = env.shards
 
     def run_rollouts(k):
@@ -447,11 +453,14 @@ def run_ours(args):
         adv = dd.gae(pbuf["reward"], vals, dones)
         nadv = torch.empty_like(adv)
 
+        mom_f = torch.zeros(3, dtype=torch.float64, device=dev)
+
         def run_ppo_tail(kk):
             for _ in range(kk):
                 dd.rollout_values(vblob, pbuf["obs"], final_obs)
-                dd.gae(pbuf["reward"], vals, dones, out=adv)
-                dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
+                mom_f.zero_()
+                dd.gae(pbuf["reward"], vals, dones, out=adv, moments=mom_f)        # scan + advantage moments in one pass
+                dd.normalize_advantages(adv, reduce=ws > 1, out=nadv, moments=mom_f)
         ms_tail = timed(lambda: run_ppo_tail(1), lambda: run_ppo_tail(reps_p))
         launches += 5 * (reps_p + 1)
         # each kernel of the tail alone, against its own roofline.  Working sets: critic 983 MB of observations, GAE 213 MB
@@ -468,7 +477,7 @@ def run_ours(args):
                 dd.value_forward(vblob, pbuf["obs"], out=vals[:TP])
         def t_gae(kk):
             for _ in range(kk):
-                dd.gae(pbuf["reward"], vals, dones, out=adv)
+                dd.gae(pbuf["reward"], vals, dones, out=adv, moments=mom_f)
         def t_mom(kk):
             for j in range(kk):
                 dd.advantage_moments(rot[j % 4], out=mom)
@@ -487,8 +496,8 @@ def run_ours(args):
         others["critic_value_forward"] = {"bound": "tensor", "achieved": vtf, "peak": PK["bf16_sustained"], "unit": "TFLOP/s",
                                           "frac": vtf / PK["bf16_sustained"], "ms_per_launch": ms_v, "rows": ne}
         for name, ms_, bytes_el, what in (
-                ("gae_kernel", ms_g, 13.0 + 4.0 / TP, "read reward 4 + value 4 + done 1, write advantage 4 B per element (+ the bootstrap row)"),
-                ("moments_kernel", ms_m, 4.0, "one read of the advantage buffer"),
+                ("gae_kernel", ms_g, 13.0 + 4.0 / TP, "read reward 4 + value 4 + done 1, write advantage 4 B per element (+ the bootstrap row); the advantage moments are accumulated in the same pass"),
+                ("moments_kernel", ms_m, 4.0, "one read of a [T,N] buffer (stand-alone K4; the PPO tail gets its moments from the GAE pass)"),
                 ("normalize_kernel", ms_n, 8.0, "read 4 + write 4 B per element")):
             ach = ne * bytes_el / (ms_ * 1e-3) / 1e9
             others[name] = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
@@ -509,8 +518,9 @@ def run_ours(args):
             penv.reset_stats()
             dd.policy_rollout(penv, b_it, TP, sample=True, want="arldo", out=pbuf)
             dd.rollout_values(vb_it, pbuf["obs"], penv.observe())
-            dd.gae(pbuf["reward"], vals, dones, out=adv)
-            dd.normalize_advantages(adv, reduce=ws > 1, out=nadv)
+            mom_f.zero_()
+            dd.gae(pbuf["reward"], vals, dones, out=adv, moments=mom_f)
+            dd.normalize_advantages(adv, reduce=ws > 1, out=nadv, moments=mom_f)
             st_it = penv.stats(reduce=ws > 1)                  # device -> host: synchronises
             t_it.append(time.perf_counter() - t0)
         launches += 9 * len(t_it)
@@ -557,10 +567,8 @@ def run_ours(args):
     e2e_modes = {}
     for mode in ("copy", "zero_copy"):
         def run_e2e(k):
-            for j in range(k):
-                b = io[j % len(io)]
-                b["actions"].copy_(host_trace[j % env.L])    # host-side: the caller's actions of this step
-                shards[j % S].step_host(b, mode=mode)
+            for j in range(k):                               # the caller's actions of this step: a row of pinned host memory
+                shards[j % S].step_host(io[j % len(io)], mode=mode, actions=host_trace[j % env.L])
         ms_e2e = timed(lambda: run_e2e(3), lambda: run_e2e(Ke2))
         launches += Ke2 + 3
         e2e_modes[mode] = ms_e2e / Ke2
@@ -620,8 +628,8 @@ def run_ours(args):
                 "gym_step_f64": f64,
                 "gym_step_eager_api": {"value": n * Ke * ws / (ms_eager * 1e-3), "ms_per_step": ms_eager / Ke, "achieved_gbs": eg_ach,
                                        "frac": eg_ach / peak_gbs, "steps": Ke, "host_us_per_step_raw_call": host_us,
-                                       "what": "BatchedDroneEnv.step_raw called from Python once per step (dd_step_planned), single chain, "
-                                               "no graph: the path of a caller with a policy in the loop"},
+                                       "what": "ShardedDroneEnv(use_graphs=False): BatchedDroneEnv.step_raw called from Python once per step "
+                                               "(dd_step_planned) on the chain streams, no graph: the path of a caller that cannot capture"},
                 "rollout_T50_fixed_policy_bangbang": {"value": n * T_ROLL * reps * ws / (ms_roll_bb * 1e-3),
                                                       "ms_per_launch": ms_roll_bb / reps, "steps_per_launch": T_ROLL},
                 "rollout_T50_in_kernel_actions": {"value": n * T_ROLL * reps * ws / (ms_roll * 1e-3),

@@ -227,6 +227,10 @@ int dd_normalize(const float *x, float *y, const double *moments, double eps, in
 /* compute_gae (Actor_Critic_PPO.ipynb c15:L49-53) for [T][n] rewards/dones and [T+1][n] values. */
 int dd_gae(const float *rewards_tn, const float *values_t1n, const uint8_t *dones_tn, float *adv_tn,
            float *returns_tn, double gamma, double lambda, int32_t T, int64_t n, void *stream);
+/* dd_gae that also ACCUMULATES the moments (n, sum, sum of squares) of the advantages it writes into moments[3]
+ * (device doubles, nullable) in the same pass: dd_normalize can follow without dd_moments re-reading the buffer. */
+int dd_gae_moments(const float *rewards_tn, const float *values_t1n, const uint8_t *dones_tn, float *adv_tn,
+                   float *returns_tn, double *moments, double gamma, double lambda, int32_t T, int64_t n, void *stream);
 
 /* compute_returns (Policy_Gradients.ipynb: G = r + gamma * G over reversed(rewards)) for [T][n] rewards; dones_tn
  * (nullable) marks the steps that ended an episode: G restarts behind them.  float64 accumulation like the
@@ -244,26 +248,43 @@ typedef struct DDPolicy {
     const float *w3, *b3;                 /* network.9 (Linear 64->3) */
 } DDPolicy;
 
-#define DD_POLICY_BLOB_BYTES 66832        /* device workspace filled by dd_policy_pack */
+#define DD_POLICY_BLOB_BYTES 65568        /* device workspace filled by dd_policy_pack */
 #define DD_ACTION_THRESHOLD 0             /* action = probs > 0.5        (c18:L24-25) */
 #define DD_ACTION_SAMPLE    1             /* action ~ Bernoulli(probs)   (c16:L61-63), Philox */
 
+/* 16-bit format of the tensor-core operands (weight images and hidden activations; accumulation is fp32):
+ *   DD_OPERANDS_FP16  10 mantissa bits: 8x lower rounding error than bf16 at the same MMA rate.  Needs the packed
+ *                     network to fit the fp16 range, which dd_policy_pack verifies from the parameters alone
+ *                     (|normalised activation| <= sqrt(N), so max |activation| <= sqrt(N) + max |beta / gamma|):
+ *                     LayerNorm |gamma| in [2^-6, 2^6], |beta / gamma| <= 1024, weight-image maxima in [2^-8, 1024];
+ *   DD_OPERANDS_BF16  8 exponent bits: any fp32 network (gamma = 0, huge beta / gamma ...);
+ *   DD_OPERANDS_AUTO  fp16 when the check passes, else bf16 -- what dd_policy_pack / dd_value_pack use. */
+#define DD_OPERANDS_AUTO 0
+#define DD_OPERANDS_BF16 1
+#define DD_OPERANDS_FP16 2
+
 /* The per-column fp32 parameters the CUDA cores apply after each tensor-core layer.  HOST memory: the
  * launch passes them by value (kernel-argument constant bank), so every thread reads them as uniform
- * operands instead of replicating shared-memory loads.  Filled by dd_policy_pack. */
+ * operands instead of replicating shared-memory loads.  Filled by dd_policy_pack.
+ * With s = sign(gamma), g = |gamma| (floored at 1e-12): the accumulator of a layer is s (x - mean x), the activation
+ * handed to the next layer is relu(s (x - mean x) rstd + beta / g), and g rides in the next layer's weight image
+ * (relu(gamma n + beta) = g relu(s n + beta / g)); for the last hidden layer g is folded into w3. */
 typedef struct DDPolicyConsts {
-    float inv_gamma0[128], beta0[128];    /* network.1: 1 / LayerNorm.weight (|w| floored at 1e-12), LayerNorm.bias */
-    float inv_gamma1[128], beta1[128];    /* network.4 */
-    float inv_gamma2[64],  beta2[64];     /* network.7 */
-    float w3[3][64];                      /* network.9.weight */
+    float beta0[128];                     /* network.1: LayerNorm.bias / |LayerNorm.weight| */
+    float beta1[128];                     /* network.4 */
+    float beta2[64];                      /* network.7 */
+    float w3[3][64];                      /* network.9.weight x |network.7.weight| (column-wise) */
     float b3[4];                          /* network.9.bias (+ pad) */
+    int32_t operands;                     /* DD_OPERANDS_BF16 / DD_OPERANDS_FP16: what the blob's images are */
+    int32_t reserved[3];
 } DDPolicyConsts;
 
-/* fp32 torch parameters (DEVICE pointers) -> `blob` (device, 16-byte aligned): bf16 tensor-core operand
- * images with the LayerNorm centring, gamma and the biases folded in; and `consts` (HOST).  This is the one
- * entry point that synchronises `stream` (it copies 3.3 KB back to fill `consts`); call it once per policy
- * update. */
+/* fp32 torch parameters (DEVICE pointers) -> `blob` (device, 16-byte aligned): 16-bit tensor-core operand
+ * images with the LayerNorm centring, the sign of gamma, the previous layer's |gamma| and the biases folded in;
+ * and `consts` (HOST).  This is the one entry point that synchronises `stream` (it copies 2 KB back to fill
+ * `consts`); call it once per policy update.  dd_policy_pack == dd_policy_pack_ex(..., head 3, DD_OPERANDS_AUTO). */
 int dd_policy_pack(const DDPolicy *p, void *blob, DDPolicyConsts *consts, void *stream);
+int dd_policy_pack_ex(const DDPolicy *p, int32_t head, int32_t operands, void *blob, DDPolicyConsts *consts, void *stream);
 
 /* probs[n][3] = policy(obs[n][15]) through the same tcgen05 path the rollout uses (parity hook).  Persistent
  * over the rows: any n up to DD_MAX_ENVS_PER_CALL, e.g. a whole [T*N][15] rollout buffer. */

@@ -25,12 +25,13 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--want", default="arldo")
     ap.add_argument("--threshold", action="store_true")
+    ap.add_argument("--operands", default="auto", choices=["auto", "bf16", "fp16"], help="16-bit format of the tensor-core operands")
     ap.add_argument("--values", action="store_true", help="also time critic values over the buffer, GAE, normalisation")
     args = ap.parse_args()
     dev = "cuda:0"
     d = np.load(os.path.join(ROOT, "tests", "golden", "policy_v1.npz"))
     sd = {k: torch.from_numpy(d[k]) for k in d.files if k.startswith("network")}
-    blob = dd.PolicyBlob(sd, device=dev)
+    blob = dd.PolicyBlob(sd, device=dev, operands=args.operands)
     env = dd.BatchedDroneEnv(args.envs, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
                              max_steps=250, auto_reset=True, dtype=torch.float32)
     env.reset()
@@ -39,18 +40,18 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for j in range(args.reps):
-        dd.policy_rollout(env, blob, args.T, sample=not args.threshold, t0=(j + 1) * args.T, want=args.want, out=buf)
+        dd.policy_rollout(env, blob, args.T, sample=not args.threshold, want=args.want, out=buf)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
     steps = args.envs * args.T
-    out = {"kernel": "policy_rollout_kernel", "envs": args.envs, "T": args.T, "want": args.want,
+    out = {"kernel": "policy_rollout_kernel", "operands": blob.operand_dtype, "lib": os.environ.get("DRONE_B200_LIB", "default"), "envs": args.envs, "T": args.T, "want": args.want,
            "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
            "mlp_tflops": steps * 53376 / ms * 1e3 / 1e12, "stats": env.stats()}
     if args.values and "obs" in buf:
         # the critic over the whole rollout buffer + bootstrap row, then GAE and advantage normalisation
         c = np.load(os.path.join(ROOT, "tests", "golden", "critic_v1.npz"))
-        vblob = dd.ValueBlob({k: torch.from_numpy(c[k]) for k in c.files if k.startswith("network")}, device=dev)
+        vblob = dd.ValueBlob({k: torch.from_numpy(c[k]) for k in c.files if k.startswith("network")}, device=dev, operands=args.operands)
         final_obs = env.observe().clone()
         vals = dd.rollout_values(vblob, buf["obs"], final_obs)
         done = (buf["done"] != 0).to(torch.uint8)

@@ -39,6 +39,7 @@ ENV_RECORD_DOUBLES = 32
 SHAPING_PPO, SHAPING_PG = 0, 1
 RETURN_FIXED_SCALE = 1048576.0
 LAUNCH_PDL, LAUNCH_BLOCK_128, LAUNCH_BLOCK_512 = 0x01, 0x10, 0x20
+OPERANDS_AUTO, OPERANDS_BF16, OPERANDS_FP16 = 0, 1, 2
 
 _PARAM_FIELDS = (
     "width", "height", "gravity", "drag", "angular_drag", "drone_height", "main_thrust", "side_thrust",
@@ -85,10 +86,9 @@ class DDPolicy(C.Structure):
 
 class DDPolicyConsts(C.Structure):
     """Host-side per-column parameters of the fused policy kernel (passed by value at launch)."""
-    _fields_ = [("inv_gamma0", C.c_float * 128), ("beta0", C.c_float * 128),
-                ("inv_gamma1", C.c_float * 128), ("beta1", C.c_float * 128),
-                ("inv_gamma2", C.c_float * 64), ("beta2", C.c_float * 64),
-                ("w3", (C.c_float * 64) * 3), ("b3", C.c_float * 4)]
+    _fields_ = [("beta0", C.c_float * 128), ("beta1", C.c_float * 128), ("beta2", C.c_float * 64),
+                ("w3", (C.c_float * 64) * 3), ("b3", C.c_float * 4),
+                ("operands", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 def nvcc_path() -> str:
@@ -179,8 +179,12 @@ def lib():
     L.dd_normalize.argtypes = [vp, vp, vp, C.c_double, i64, vp]
     L.dd_gae.restype = C.c_int
     L.dd_gae.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp]
+    L.dd_gae_moments.restype = C.c_int
+    L.dd_gae_moments.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp]
     L.dd_policy_pack.restype = C.c_int
     L.dd_policy_pack.argtypes = [C.POINTER(DDPolicy), vp, C.POINTER(DDPolicyConsts), vp]
+    L.dd_policy_pack_ex.restype = C.c_int
+    L.dd_policy_pack_ex.argtypes = [C.POINTER(DDPolicy), i32, i32, vp, C.POINTER(DDPolicyConsts), vp]
     L.dd_policy_forward.restype = C.c_int
     L.dd_policy_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
     L.dd_discounted_returns.restype = C.c_int
@@ -214,7 +218,7 @@ def default_params() -> DDParams:
 EXPORTS = (
     "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_step_plan", "dd_step_planned",
     "dd_rollout", "dd_rollout_shaped",
-    "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae",
-    "dd_policy_pack", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env", "dd_discounted_returns",
+    "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae", "dd_gae_moments",
+    "dd_policy_pack", "dd_policy_pack_ex", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env", "dd_discounted_returns",
 )
 HOST_TWIN_EXPORTS = ("dd_host_abi_version", "dd_reset_host", "dd_step_host", "dd_rollout_host")

@@ -14,15 +14,20 @@
 //     memory (UMMA K-major, no-swizzle canonical layout), fp32 accumulators in TMEM (128 columns
 //     per tile, 512 = the whole TMEM per CTA), issued by one elected thread per tile and tracked with
 //     `tcgen05.commit` -> mbarrier;
-//   * LayerNorm is folded into the GEMM operands by dd_policy_pack.  With C = I - 11^T/N (centring
-//     over the N outputs) and G = diag(gamma): the weight image is bf16(G C W), the bias G C b rides in
-//     an extra K = 16 block (a constant "ones" A block x a [N][16] image holding the bias split into
-//     bf16 hi + lo), so the accumulator row is  x''_j = gamma_j (x_j - mean(x)).  What is left for the
-//     CUDA cores is  var = 1/N sum_j (x''_j / gamma_j)^2  (pass 1: FMUL2 + FFMA2 per column pair) and
-//     y_j = x''_j * rstd + beta_j  (pass 2: one FFMA2, ReLU inside the bf16 conversion), i.e. 4
-//     instructions per pair instead of 7;
-//   * 1/gamma, beta and the last Linear travel by value in the kernel argument (DDPolicyConsts): after
-//     unrolling every access is c[0][imm] -> LDCU.128 -> a uniform-register operand of FFMA2 / FMUL2, no
+//   * LayerNorm is folded into the GEMM operands by dd_policy_pack.  With C = I - 11^T/N (centring over
+//     the N outputs), S = diag(sign gamma), g = |gamma| and g_prev the |gamma| of the PREVIOUS LayerNorm:
+//     the weight image is f16(S C W diag(g_prev)), the bias S C b rides in an extra K = 16 block (a constant
+//     "ones" A block x a [N][16] image holding the bias split into hi + lo), so the accumulator row is
+//     x'_j = s_j (x_j - mean x).  relu(gamma n + beta) = g relu(s n + beta / g): the activation handed on is
+//     a_j = relu(x'_j rstd + beta_j / g_j) and g_j is already in the next layer's image (in w3 for the last
+//     hidden layer).  What is left for the CUDA cores is  var = 1/N sum_j x'_j^2  (pass 1: ONE FFMA2 per column
+//     pair) and a_j (pass 2: one FFMA2, ReLU inside the 16-bit conversion): 3 instructions per pair; round 1
+//     kept gamma in the image of its own layer and paid an FMUL2 by 1/gamma per pair in pass 1 (+160 FMUL2 and
+//     80 LDCU per env-step, 14 % of the kernel's instructions);
+//   * the 16-bit operand format is fp16 when the packed network fits its range (checked by dd_policy_pack from
+//     the parameters: 10 mantissa bits, 8x lower rounding error than bf16 at the same MMA rate), bf16 otherwise;
+//   * beta / g and the last Linear travel by value in the kernel argument (DDPolicyConsts): after
+//     unrolling every access is c[0][imm] -> LDCU.128 -> a uniform-register operand of FFMA2, no
 //     shared-memory loads in the epilogues;
 //   * the first layer runs in split-bf16 precision: observation and layer-0 image are hi + lo bf16 pairs and
 //     D = x_hi W_hi + x_hi W_lo + x_lo W_hi (three K = 16 MMAs instead of one, ~16 mantissa bits): the input
@@ -47,6 +52,8 @@
 // the tensor pipe is ~40 % busy.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 #include "drone_device.cuh"
@@ -71,17 +78,22 @@ constexpr int kW1bOff = kW1Off + kH2 * kH1 * 2;            // [128][16]  col 0/1
 constexpr int kW2Off = kW1bOff + kH2 * 16 * 2;             // [64][128]  G2 C2 W2
 constexpr int kW2bOff = kW2Off + kH3 * kH2 * 2;            // [64][16]   col 0/1 = hi/lo of G2 C2 b2
 constexpr int kW0loOff = kW2bOff + kH3 * 16 * 2;           // [128][16]  low halves of the layer-0 image (split bf16)
-constexpr int kParOff = kW0loOff + kH1 * kInPad * 2;       // fp32 parameters
-// fp32 parameter order: 1/gamma and beta per LayerNorm, then the last Linear
-constexpr int pIg0 = 0, pBe0 = 128, pIg1 = 256, pBe1 = 384, pIg2 = 512, pBe2 = 576, pW3 = 640, pB3 = 832,
-              kParFloats = 836;
-constexpr int kBlobBytes = kParOff + kParFloats * 4;       // 66,832
+constexpr int kParOff = kW0loOff + kH1 * kInPad * 2;       // a DDPolicyConsts image (fp32 parameters + operand format)
+// word offsets inside it: beta / |gamma| per LayerNorm, then the last Linear (x |gamma| of the last LayerNorm), format
+constexpr int pBe0 = 0, pBe1 = 128, pBe2 = 256, pW3 = 320, pB3 = 512, pFmt = 516, kParWords = 520;
+constexpr int kBlobBytes = kParOff + kParWords * 4;        // 65,568
 static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
 static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
-static_assert(sizeof(DDPolicyConsts) == kParFloats * 4, "the blob's fp32 section is a DDPolicyConsts image");
+static_assert(sizeof(DDPolicyConsts) == kParWords * 4, "the blob's parameter section is a DDPolicyConsts image");
+static_assert(offsetof(DDPolicyConsts, beta1) == pBe1 * 4 && offsetof(DDPolicyConsts, beta2) == pBe2 * 4 &&
+              offsetof(DDPolicyConsts, w3) == pW3 * 4 && offsetof(DDPolicyConsts, b3) == pB3 * 4 &&
+              offsetof(DDPolicyConsts, operands) == pFmt * 4, "DDPolicyConsts layout");
 constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this is treated as +-1e-12
 #ifndef DD_K5_CHUNK
 #define DD_K5_CHUNK 16
+#endif
+#ifndef DD_K5_FLUSH_AT
+#define DD_K5_FLUSH_AT 1                       // under which MMA of the next step the deferred outputs of a step are written
 #endif
 constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (8, 16 or 32; 16 measured best)
 
@@ -174,10 +186,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// Instruction descriptor, kind::f16: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major,
-// N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor, kind::f16: D fp32 (bit 4), A format at [7,10) and B format at [10,13) (0 = fp16, 1 = bf16),
+// both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool f16) {
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -248,25 +260,37 @@ template <int CH>
 __device__ __forceinline__ float2 f2_of(const TmemChunk<CH>& t, int pair) {
     return make_float2(__uint_as_float(t.r[2 * pair]), __uint_as_float(t.r[2 * pair + 1]));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);    // .x = lo (low 16 bits)
-    return *reinterpret_cast<const uint32_t*>(&p);
-}
-// max(x, 0) fused into the bf16x2 conversion (F2FP.RELU): the ReLU of the hidden layers is free
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+// two fp32 -> one 32-bit word of two 16-bit operands (`lo` in the low half); F16: fp16, else bf16
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
     uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    if constexpr (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else               asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
+}
+// max(x, 0) fused into the conversion (F2FP.RELU): the ReLU of the hidden layers is free
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi) {
+    uint32_t d;
+    if constexpr (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else               asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// the two halves of a packed word back as fp32 (for the split hi + lo first layer)
+template <bool F16>
+__device__ __forceinline__ float2 unpack16(uint32_t w) {
+    if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
 // ---- one hidden layer's epilogue: LayerNorm over the N columns of my accumulator row ----------------
-// The accumulator holds x''_j = gamma_j (x_j - mean x) (see the header).  Pass 1: sum of (x''_j / gamma_j)^2
-// -> rstd.  Pass 2: y_j = x''_j rstd + beta_j, handed to sink(chunk, y[32]) BEFORE the ReLU (the sink applies
-// it: for free inside the bf16 conversion for layers 1-2, as FMNMX for the last hidden layer).  All
-// element-wise arithmetic is packed fp32x2 (FMUL2 / FFMA2, new on sm_100).  The TMEM reads are double
-// buffered: chunk c+1 (and pass 2's first chunk) is in flight while chunk c is processed.
+// The accumulator holds x'_j = s_j (x_j - mean x) (see the header).  Pass 1: sum of x'_j^2 -> rstd (one FFMA2 per
+// column pair).  Pass 2: y_j = x'_j rstd + beta_j / g_j, handed to sink(chunk, y[CH]) BEFORE the ReLU (the sink applies
+// it: for free inside the 16-bit conversion for layers 1-2, as FMNMX for the last hidden layer).  All element-wise
+// arithmetic is packed fp32x2 (FFMA2, new on sm_100).  The TMEM reads are double buffered: chunk c+1 (and pass 2's
+// first chunk) is in flight while chunk c is processed.
 template <int N, int CH, typename Sink>
-__device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gamma)[N], const float (&beta)[N], Sink sink)
+__device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&beta)[N], Sink sink)
 {
     constexpr int NC = N / CH;
     static_assert(NC % 2 == 0, "two buffers alternate over an even number of chunks");
@@ -280,12 +304,9 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gam
         buf[c & 1].wait();
         buf[(c + 1) & 1].issue(trow + (uint32_t)(((c + 1) % NC) * CH));      // next chunk / pass 2's first
 #pragma unroll
-        for (int j = 0; j < CH / 4; ++j) {
-            const int col = c * CH + 4 * j;              // compile-time after unrolling: c[0][imm] -> uniform registers
-            const float2 t0 = __fmul2_rn(f2_of(buf[c & 1], 2 * j), make_float2(inv_gamma[col], inv_gamma[col + 1]));
-            const float2 t1 = __fmul2_rn(f2_of(buf[c & 1], 2 * j + 1), make_float2(inv_gamma[col + 2], inv_gamma[col + 3]));
-            q[(2 * j) & 3] = __ffma2_rn(t0, t0, q[(2 * j) & 3]);
-            q[(2 * j + 1) & 3] = __ffma2_rn(t1, t1, q[(2 * j + 1) & 3]);
+        for (int j = 0; j < CH / 2; ++j) {
+            const float2 t = f2_of(buf[c & 1], j);
+            q[j & 3] = __ffma2_rn(t, t, q[j & 3]);
         }
     }
     const float sq = ((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y));
@@ -298,7 +319,7 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gam
         float y[CH];
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
-            const int col = c * CH + 4 * j;
+            const int col = c * CH + 4 * j;              // compile-time after unrolling: c[0][imm] -> uniform registers
             const float2 y0 = __ffma2_rn(f2_of(buf[c & 1], 2 * j), r2, make_float2(beta[col], beta[col + 1]));
             const float2 y1 = __ffma2_rn(f2_of(buf[c & 1], 2 * j + 1), r2, make_float2(beta[col + 2], beta[col + 3]));
             y[4 * j] = y0.x; y[4 * j + 1] = y0.y; y[4 * j + 2] = y1.x; y[4 * j + 3] = y1.y;
@@ -307,14 +328,14 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&inv_gam
     }
 }
 
-// ReLU + write CH activations of my row (K columns CH*c .. CH*c+CH-1) as bf16 into the A tile (UMMA layout)
-template <int CH>
+// ReLU + write CH activations of my row (K columns CH*c .. CH*c+CH-1) as fp16 / bf16 into the A tile (UMMA layout)
+template <int CH, bool F16>
 __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int c, const float (&y)[CH]) {
 #pragma unroll
     for (int q = 0; q < CH / 8; ++q) {                      // 16-byte K chunks
         uint4 w;
-        w.x = pack_bf16_relu(y[8 * q + 0], y[8 * q + 1]); w.y = pack_bf16_relu(y[8 * q + 2], y[8 * q + 3]);
-        w.z = pack_bf16_relu(y[8 * q + 4], y[8 * q + 5]); w.w = pack_bf16_relu(y[8 * q + 6], y[8 * q + 7]);
+        w.x = pack16_relu<F16>(y[8 * q + 0], y[8 * q + 1]); w.y = pack16_relu<F16>(y[8 * q + 2], y[8 * q + 3]);
+        w.z = pack16_relu<F16>(y[8 * q + 4], y[8 * q + 5]); w.w = pack16_relu<F16>(y[8 * q + 6], y[8 * q + 7]);
         *reinterpret_cast<uint4*>(a_tile + ((CH / 8) * c + q) * (kTile * 16) + row * 16) = w;
     }
 }
@@ -329,7 +350,8 @@ __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int
 // statistics, and exactly the action / log-prob / reward / done / observation buffers (no shaped reward, no
 // probabilities) -- with every launch-constant switch a compile-time constant: predicated-off stores, their address
 // arithmetic and the selects between modes still cost issue slots, and this kernel is bound by them.
-template <bool DEF, int CH, bool FWD, int HEAD = 3, bool FAST = false>
+// F16: the operand images in the blob and the activations are fp16 (else bf16); chosen by dd_policy_pack.
+template <bool DEF, int CH, bool FWD, int HEAD = 3, bool FAST = false, bool F16 = false>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __grid_constant__ PArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -354,7 +376,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     {   // the constant A block that carries the biases: row r = [1, 1, 0 x 14] (K chunk 0), zeros (K chunk 1)
         uint4* ones = reinterpret_cast<uint4*>(smem + kSmemOnes);
         for (int j = tid; j < kOnesBytes / 16; j += kPolThreads)
-            ones[j] = j < kTile ? make_uint4(0x3f803f80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+            ones[j] = j < kTile ? make_uint4(F16 ? 0x3c003c00u : 0x3f803f80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
 #pragma unroll
@@ -468,15 +490,16 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             write_obs(e, pflags, speed, dist, k, [&](int j, float v) { ob[j] = v; });
         }
         ob[15] = 1.0f;
-        // split bf16: hi = bf16(x), lo = bf16(x - hi); K chunks 0-1 = hi, 2-3 = lo
+        // split 16-bit: hi = f16(x), lo = f16(x - hi); K chunks 0-1 = hi, 2-3 = lo
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float x0 = ob[8 * q + 2 * j], x1 = ob[8 * q + 2 * j + 1];
-                hi[j] = pack_bf16(x0, x1);
-                lo[j] = pack_bf16(x0 - __uint_as_float(hi[j] << 16), x1 - __uint_as_float(hi[j] & 0xffff0000u));
+                hi[j] = pack16<F16>(x0, x1);
+                const float2 h = unpack16<F16>(hi[j]);
+                lo[j] = pack16<F16>(x0 - h.x, x1 - h.y);
             }
             *reinterpret_cast<uint4*>(s_a + q * (kTile * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(s_a + (2 + q) * (kTile * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -485,9 +508,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (issuer_warp && elect_one()) {
             tc_fence_after();
-            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 0u);      // x_hi W_hi
-            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0lo_addr, kH1 * 16, 128), umma_idesc(128, kH1), 1u);    // x_hi W_lo
-            umma_bf16(tmem_d, umma_desc(a_addr + 2 * (kTile * 16), kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1), 1u);   // x_lo W_hi
+            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1, F16), 0u);      // x_hi W_hi
+            umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0lo_addr, kH1 * 16, 128), umma_idesc(128, kH1, F16), 1u);    // x_hi W_lo
+            umma_bf16(tmem_d, umma_desc(a_addr + 2 * (kTile * 16), kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1, F16), 1u);   // x_lo W_hi
             umma_commit(bar);
             if (FWD) {                                       // everyone has read s_obs: fetch the next block's tile
                 const uint32_t next0 = tile0 + gridDim.x * (kGroups * kTile);
@@ -505,10 +528,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
         }
+#if DD_K5_FLUSH_AT == 1
         if (!forward_only && t > 0) flush_pending(o - a.n);
+#endif
         wait_mma(bar, phase, issuer_warp, g);
-        ln_epilogue<kH1, CH>(trow, pc.inv_gamma0, pc.beta0,
-                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
+        ln_epilogue<kH1, CH>(trow, pc.beta0,
+                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH, F16>(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (issuer_warp && elect_one()) {
@@ -521,10 +546,13 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kH1 / 16; ++j)
                 umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
-                          umma_desc(w1_addr + j * 2 * (kH2 * 16), kH2 * 16, 128), umma_idesc(128, kH2), j > 0 ? 1u : 0u);
-            umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w1b_addr, kH2 * 16, 128), umma_idesc(128, kH2), 1u);
+                          umma_desc(w1_addr + j * 2 * (kH2 * 16), kH2 * 16, 128), umma_idesc(128, kH2, F16), j > 0 ? 1u : 0u);
+            umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w1b_addr, kH2 * 16, 128), umma_idesc(128, kH2, F16), 1u);
             umma_commit(bar);
         }
+#if DD_K5_FLUSH_AT == 2
+        if (!forward_only && t > 0) flush_pending(o - a.n);  // under the second (longest) MMA: the previous step's deferred outputs
+#endif
         U4 rnd = {0u, 0u, 0u, 0u};                           // under the second MMA: this step's Philox draws
         if (!forward_only && !thresholded) {
             rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
@@ -532,8 +560,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             pin(rnd.a); pin(rnd.b); pin(rnd.c);
         }
         wait_mma(bar, phase, issuer_warp, g);
-        ln_epilogue<kH2, CH>(trow, pc.inv_gamma1, pc.beta1,
-                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH>(s_a, row, c, y); });
+        ln_epilogue<kH2, CH>(trow, pc.beta1,
+                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH, F16>(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
         if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         fence_async_smem(); tc_fence_before(); group_bar(g);
@@ -542,8 +570,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kH2 / 16; ++j)
                 umma_bf16(tmem_d, umma_desc(a_addr + j * 2 * (kTile * 16), kTile * 16, 128),
-                          umma_desc(w2_addr + j * 2 * (kH3 * 16), kH3 * 16, 128), umma_idesc(128, kH3), j > 0 ? 1u : 0u);
-            umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3), 1u);
+                          umma_desc(w2_addr + j * 2 * (kH3 * 16), kH3 * 16, 128), umma_idesc(128, kH3, F16), j > 0 ? 1u : 0u);
+            umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3, F16), 1u);
             umma_commit(bar);
         }
         float s_pre = 0.f, c_pre = 1.f;                      // under the third MMA: sin / cos of the pre-update angle
@@ -551,7 +579,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         wait_mma(bar, phase, issuer_warp, g);
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
-        ln_epilogue<kH3, CH>(trow, pc.inv_gamma2, pc.beta2, [&](int c, const float (&y)[CH]) {
+        ln_epilogue<kH3, CH>(trow, pc.beta2, [&](int c, const float (&y)[CH]) {
 #pragma unroll
             for (int j = 0; j < CH / 4; ++j) {
                 const float2 h0 = make_float2(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f));      // ReLU
@@ -648,71 +676,117 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 }
 
 // ---- fp32 torch parameters -> blob ---------------------------------------------------------------
-// One CTA.  For a layer x = W a + b followed by LayerNorm(gamma, beta) over its N outputs:
-//   image = bf16( gamma_n (W[n][k] - mean_n' W[n'][k]) ),  bias'' = gamma_n (b[n] - mean b)  (bf16 hi + lo),
-//   1/gamma and beta stay fp32.  |gamma| < 1e-12 is replaced by +-1e-12: the pre-activation then differs
-//   from beta by < 1.2e-11 (|normalised value| <= sqrt(N)), far below the bf16 activation rounding.
-__device__ __forceinline__ float gamma_clamped(float g) { return fabsf(g) < kGammaFloor ? copysignf(kGammaFloor, g) : g; }
+// One CTA.  For a layer x = W a + b followed by LayerNorm(gamma, beta) over its N outputs, with s = sign(gamma),
+// g = max(|gamma|, 1e-12) and g_prev the g of the previous LayerNorm (1 for the first layer):
+//   image[n][k] = f16( s_n (W[n][k] - mean_n' W[n'][k]) g_prev_k ),  bias image = s_n (b[n] - mean b)  (hi + lo),
+//   beta' = beta / g stays fp32 (DDPolicyConsts), the last Linear becomes w3[o][j] g_j.
+// The floor changes a pre-activation by < 1.2e-11 (|normalised value| <= sqrt(N)), far below the 16-bit rounding.
+// Operand format: fp16 if the network provably fits (see DD_OPERANDS_* in the header), else bf16.
+__device__ __forceinline__ float gamma_abs(float g) { const float a = fabsf(g); return a < kGammaFloor ? kGammaFloor : a; }
+__device__ __forceinline__ float gamma_sign(float g) { return g < 0.f ? -1.f : 1.f; }
 __device__ __forceinline__ int img_at(int N, int n, int kk) { return (kk / 8) * (N * 8) + n * 8 + (kk % 8); }   // element index
 
-__global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, int head, uint8_t* blob)
-{
-    __shared__ float s_mean[129];                          // column means of the current layer; [128] = mean of the bias
-    const int tid = threadIdx.x, nth = blockDim.x;
-    __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(blob + kW0Off);
-    __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(blob + kW1Off);
-    __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>(blob + kW1bOff);
-    __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(blob + kW2Off);
-    __nv_bfloat16* w2b = reinterpret_cast<__nv_bfloat16*>(blob + kW2bOff);
-    __nv_bfloat16* w0lo = reinterpret_cast<__nv_bfloat16*>(blob + kW0loOff);
-    float* par = reinterpret_cast<float*>(blob + kParOff);
+template <bool F16> __device__ __forceinline__ float round16(float v) {
+    if constexpr (F16) return __half2float(__float2half_rn(v));
+    else return __bfloat162float(__float2bfloat16_rn(v));
+}
+template <bool F16> __device__ __forceinline__ void store16(uint8_t* img, int idx, float v) {
+    if constexpr (F16) reinterpret_cast<__half*>(img)[idx] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(img)[idx] = __float2bfloat16_rn(v);
+}
 
-    // layer 0: [W0 | b0] is one [128][16] matrix (obs[15] := 1)
-    auto src0 = [&](int n, int kk) { return kk < kIn ? p.w0[n * kIn + kk] : p.b0[n]; };
-    for (int kk = tid; kk < kInPad; kk += nth) {
-        double m = 0.0;
-        for (int n = 0; n < kH1; ++n) m += (double)src0(n, kk);
-        s_mean[kk] = (float)(m / kH1);
-    }
-    __syncthreads();
+struct PackLayer { const float *w, *b, *g, *gprev; int N, K; };   // K real inputs (15 or 128); gprev == nullptr: ones
+
+__device__ __forceinline__ float pack_entry(const PackLayer& L, const float* mean, int n, int kk)
+{   // kk == L.K: the bias column
+    const float s = gamma_sign(L.g[n]);
+    if (kk == L.K) return s * (L.b[n] - mean[L.K]);
+    const float c = L.gprev ? gamma_abs(L.gprev[kk]) : 1.0f;
+    return s * (L.w[n * L.K + kk] - mean[kk]) * c;
+}
+
+template <bool F16>
+__device__ void pack_write_images(const PackLayer (&Ls)[3], const float (*mean)[129], uint8_t* blob, int tid, int nth)
+{
+    // layer 0: [W0 | b0] is one [128][16] matrix (obs[15] := 1), split hi + lo
     for (int j = tid; j < kH1 * kInPad; j += nth) {
         const int n = j / kInPad, kk = j % kInPad;
-        const float v = gamma_clamped(p.g0[n]) * (src0(n, kk) - s_mean[kk]);
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        w0[img_at(kH1, n, kk)] = hi;
-        w0lo[img_at(kH1, n, kk)] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const float v = pack_entry(Ls[0], mean[0], n, kk);
+        const float hi = round16<F16>(v);
+        store16<F16>(blob + kW0Off, img_at(kH1, n, kk), v);
+        store16<F16>(blob + kW0loOff, img_at(kH1, n, kk), v - hi);
+    }
+    // layers 1, 2: K = 128 weight image + the bias block (col 0 = hi, col 1 = lo against the constant ones block)
+    const int woff[3] = {0, kW1Off, kW2Off}, boff[3] = {0, kW1bOff, kW2bOff};
+    for (int l = 1; l < 3; ++l) {
+        const PackLayer& L = Ls[l];
+        for (int j = tid; j < L.N * 128; j += nth) {
+            const int n = j / 128, kk = j % 128;
+            store16<F16>(blob + woff[l], img_at(L.N, n, kk), pack_entry(L, mean[l], n, kk));
+        }
+        for (int j = tid; j < L.N * 16; j += nth) {
+            const int n = j / 16, kk = j % 16;
+            const float v = pack_entry(L, mean[l], n, 128);
+            const float hi = round16<F16>(v);
+            store16<F16>(blob + boff[l], img_at(L.N, n, kk), kk == 0 ? v : (kk == 1 ? v - hi : 0.f));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, int head, int operands, uint8_t* blob)
+{
+    __shared__ float s_mean[3][129];                       // per layer: column means over the outputs; [K] = mean of the bias
+    __shared__ unsigned s_imax[3], s_bmax, s_gmin, s_gmax;  // maxima / minima as the bit patterns of non-negative floats
+    __shared__ int s_fmt;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const PackLayer Ls[3] = {{p.w0, p.b0, p.g0, nullptr, kH1, kIn}, {p.w1, p.b1, p.g1, p.g0, kH2, kH1}, {p.w2, p.b2, p.g2, p.g1, kH3, kH2}};
+    if (tid < 3) s_imax[tid] = 0u;
+    if (tid == 0) { s_bmax = 0u; s_gmin = 0x7f800000u; s_gmax = 0u; }
+    for (int l = 0; l < 3; ++l) {
+        const PackLayer& L = Ls[l];
+        for (int kk = tid; kk <= L.K; kk += nth) {
+            double m = 0.0;
+            for (int n = 0; n < L.N; ++n) m += (double)(kk < L.K ? L.w[n * L.K + kk] : L.b[n]);
+            s_mean[l][kk] = (float)(m / L.N);
+        }
     }
     __syncthreads();
-    // layers 1, 2: K = 128 weight image + the bias block
-    auto hidden = [&](const float* w, const float* b, const float* g, int N, __nv_bfloat16* img, __nv_bfloat16* bimg) {
-        for (int kk = tid; kk <= 128; kk += nth) {
-            double m = 0.0;
-            for (int n = 0; n < N; ++n) m += (double)(kk < 128 ? w[n * 128 + kk] : b[n]);
-            s_mean[kk] = (float)(m / N);
+    // ---- can the images and activations live in fp16?  (NaN / inf parameters fail every comparison -> bf16) ----
+    for (int l = 0; l < 3; ++l) {
+        const PackLayer& L = Ls[l];
+        unsigned mx = 0u;
+        for (int j = tid; j < L.N * (L.K + 1); j += nth) {
+            const float v = fabsf(pack_entry(L, s_mean[l], j / (L.K + 1), j % (L.K + 1)));
+            mx = max(mx, v == v ? __float_as_uint(v) : 0x7f800000u);
         }
-        __syncthreads();
-        for (int j = tid; j < N * 128; j += nth) {
-            const int n = j / 128, kk = j % 128;
-            img[img_at(N, n, kk)] = __float2bfloat16_rn(gamma_clamped(g[n]) * (w[j] - s_mean[kk]));
+        atomicMax(&s_imax[l], mx);
+        const float* be = l == 0 ? p.be0 : (l == 1 ? p.be1 : p.be2);
+        for (int j = tid; j < L.N; j += nth) {
+            const float g = gamma_abs(L.g[j]), bp = fabsf(be[j] / g);
+            atomicMax(&s_gmax, g == g ? __float_as_uint(g) : 0x7f800000u);
+            atomicMin(&s_gmin, __float_as_uint(g));
+            atomicMax(&s_bmax, bp == bp ? __float_as_uint(bp) : 0x7f800000u);
         }
-        for (int j = tid; j < N * 16; j += nth) {
-            const int n = j / 16, kk = j % 16;
-            const float v = gamma_clamped(g[n]) * (b[n] - s_mean[128]);
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-            bimg[img_at(N, n, kk)] = kk == 0 ? hi : (kk == 1 ? lo : __float2bfloat16_rn(0.f));
-        }
-        __syncthreads();
-    };
-    hidden(p.w1, p.b1, p.g1, kH2, w1, w1b);
-    hidden(p.w2, p.b2, p.g2, kH3, w2, w2b);
-    for (int j = tid; j < 128; j += nth) {
-        par[pIg0 + j] = 1.0f / gamma_clamped(p.g0[j]); par[pBe0 + j] = p.be0[j];
-        par[pIg1 + j] = 1.0f / gamma_clamped(p.g1[j]); par[pBe1 + j] = p.be1[j];
     }
-    for (int j = tid; j < 64; j += nth) { par[pIg2 + j] = 1.0f / gamma_clamped(p.g2[j]); par[pBe2 + j] = p.be2[j]; }
-    for (int j = tid; j < kOut * kH3; j += nth) par[pW3 + j] = j < head * kH3 ? p.w3[j] : 0.f;   // head rows of [head][64]
+    __syncthreads();
+    if (tid == 0) {
+        bool ok = __uint_as_float(s_gmin) >= 0.015625f && __uint_as_float(s_gmax) <= 64.f && __uint_as_float(s_bmax) <= 1024.f;
+        for (int l = 0; l < 3; ++l) ok = ok && __uint_as_float(s_imax[l]) <= 1024.f && __uint_as_float(s_imax[l]) >= 0.00390625f;
+        s_fmt = (operands != DD_OPERANDS_BF16 && ok) ? DD_OPERANDS_FP16 : DD_OPERANDS_BF16;
+    }
+    __syncthreads();
+    if (s_fmt == DD_OPERANDS_FP16) pack_write_images<true>(Ls, s_mean, blob, tid, nth);
+    else pack_write_images<false>(Ls, s_mean, blob, tid, nth);
+
+    float* par = reinterpret_cast<float*>(blob + kParOff);
+    for (int j = tid; j < 128; j += nth) {
+        par[pBe0 + j] = p.be0[j] / gamma_abs(p.g0[j]);
+        par[pBe1 + j] = p.be1[j] / gamma_abs(p.g1[j]);
+    }
+    for (int j = tid; j < 64; j += nth) par[pBe2 + j] = p.be2[j] / gamma_abs(p.g2[j]);
+    for (int j = tid; j < kOut * kH3; j += nth) par[pW3 + j] = j < head * kH3 ? p.w3[j] * gamma_abs(p.g2[j % kH3]) : 0.f;   // head rows of [head][64]
     for (int j = tid; j < 4; j += nth) par[pB3 + j] = j < head ? p.b3[j] : 0.f;
+    if (tid < 4) reinterpret_cast<int32_t*>(par)[pFmt + tid] = tid == 0 ? s_fmt : 0;
 }
 
 static bool pol_params_default(const DDParams& p)
@@ -729,8 +803,10 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
     int grid = blocks;
     DeviceGuard guard(st, pa.blob);                         // the device that owns the stream (or the blob)
     if (guard.err != cudaSuccess) return (int)guard.err;
+    const bool f16 = pa.pc.operands == DD_OPERANDS_FP16;
     if (forward) {
-        kern = pa.head == 1 ? policy_rollout_kernel<true, kChunk, true, 1> : policy_rollout_kernel<true, kChunk, true, 3>;
+        kern = pa.head == 1 ? (f16 ? policy_rollout_kernel<true, kChunk, true, 1, false, true> : policy_rollout_kernel<true, kChunk, true, 1, false, false>)
+                            : (f16 ? policy_rollout_kernel<true, kChunk, true, 3, false, true> : policy_rollout_kernel<true, kChunk, true, 3, false, false>);
         int sms = 0;
         const cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, guard.dev);
         if (e != cudaSuccess) return (int)e;
@@ -739,8 +815,9 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
     } else {
         const bool fast = pa.mode == DD_ACTION_SAMPLE && pa.inv_temperature == 1.0f && pa.auto_reset && pa.a.stats &&
                           pa.actions_tn && pa.logp_tn && pa.reward_tn && pa.done_tn && pa.obs_tn && !pa.shaped_tn && !pa.probs_tn;
-        kern = def ? (fast ? policy_rollout_kernel<true, kChunk, false, 3, true> : policy_rollout_kernel<true, kChunk, false, 3, false>)
-                   : (fast ? policy_rollout_kernel<false, kChunk, false, 3, true> : policy_rollout_kernel<false, kChunk, false, 3, false>);
+#define DD_K5(DEF_, FAST_) (f16 ? policy_rollout_kernel<DEF_, kChunk, false, 3, FAST_, true> : policy_rollout_kernel<DEF_, kChunk, false, 3, FAST_, false>)
+        kern = def ? (fast ? DD_K5(true, true) : DD_K5(true, false)) : (fast ? DD_K5(false, true) : DD_K5(false, false));
+#undef DD_K5
     }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (err != cudaSuccess) return (int)err;
@@ -748,26 +825,33 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
     return (int)cudaGetLastError();
 }
 
-static int pack_common(const DDPolicy* p, int head, void* blob, DDPolicyConsts* consts, void* stream)
+static int pack_common(const DDPolicy* p, int head, int operands, void* blob, DDPolicyConsts* consts, void* stream)
 {
     if (!p || !blob || !consts) return DD_E_NULL;
+    if (head != 1 && head != 3) return DD_E_RANGE;
+    if (operands != DD_OPERANDS_AUTO && operands != DD_OPERANDS_BF16 && operands != DD_OPERANDS_FP16) return DD_E_RANGE;
     const float* const* q = reinterpret_cast<const float* const*>(p);
     for (int j = 0; j < 14; ++j) if (!q[j]) return DD_E_NULL;
     if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
     DeviceGuard guard((cudaStream_t)stream, blob);
     if (guard.err != cudaSuccess) return (int)guard.err;
-    policy_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*p, head, (uint8_t*)blob);
+    policy_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*p, head, operands, (uint8_t*)blob);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
     err = cudaMemcpyAsync(consts, (const uint8_t*)blob + kParOff, sizeof(DDPolicyConsts), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (err != cudaSuccess) return (int)err;
-    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+    err = cudaStreamSynchronize((cudaStream_t)stream);
+    if (err != cudaSuccess) return (int)err;
+    // fp16 was demanded but the network does not fit its range: the blob holds bf16 images, say so
+    if (operands == DD_OPERANDS_FP16 && consts->operands != DD_OPERANDS_FP16) return DD_E_RANGE;
+    return 0;
 }
 
 static int forward_common(const void* blob, const DDPolicyConsts* consts, const float* obs, float* out, int head, int64_t n, void* stream)
 {
     if (!blob || !consts || !obs || !out) return DD_E_NULL;
     if (n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
+    if (consts->operands != DD_OPERANDS_BF16 && consts->operands != DD_OPERANDS_FP16) return DD_E_RANGE;   // not filled by dd_policy_pack
     if (reinterpret_cast<uintptr_t>(blob) & 15u) return DD_E_ALIGN;
     if (n == 0) return 0;
     PArgs pa{};
@@ -784,12 +868,17 @@ extern "C" {
 
 int dd_policy_pack(const DDPolicy* p, void* blob, DDPolicyConsts* consts, void* stream)
 {
-    return dd::pack_common(p, 3, blob, consts, stream);
+    return dd::pack_common(p, 3, DD_OPERANDS_AUTO, blob, consts, stream);
+}
+
+int dd_policy_pack_ex(const DDPolicy* p, int32_t head, int32_t operands, void* blob, DDPolicyConsts* consts, void* stream)
+{
+    return dd::pack_common(p, head, operands, blob, consts, stream);
 }
 
 int dd_value_pack(const DDPolicy* p, void* blob, DDPolicyConsts* consts, void* stream)
 {
-    return dd::pack_common(p, 1, blob, consts, stream);
+    return dd::pack_common(p, 1, DD_OPERANDS_AUTO, blob, consts, stream);
 }
 
 int dd_policy_forward(const void* blob, const DDPolicyConsts* consts, const float* obs, float* probs, int64_t n, void* stream)
@@ -809,6 +898,7 @@ int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c,
     if (!s || !p || !c || !blob || !consts) return DD_E_NULL;
     if (s->dtype != DD_F32) return DD_E_DTYPE;                 // the fused kernel is the fp32 throughput path
     if (mode != DD_ACTION_THRESHOLD && mode != DD_ACTION_SAMPLE) return DD_E_RANGE;
+    if (consts->operands != DD_OPERANDS_BF16 && consts->operands != DD_OPERANDS_FP16) return DD_E_RANGE;       // not filled by dd_policy_pack
     if (mode == DD_ACTION_SAMPLE && !(temperature > 0.0f)) return DD_E_RANGE;
     if (T < 0 || n < 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return DD_E_RANGE;
     if (n > 0 && (!s->pos_vel || !s->att_fuel || !s->platform || !s->steps || !s->episode || !s->flags)) return DD_E_NULL;

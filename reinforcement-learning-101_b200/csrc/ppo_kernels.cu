@@ -18,6 +18,10 @@ namespace dd {
 constexpr int kRedBlock = 256;
 constexpr int kSMs = 148;
 
+// Programmatic dependent launch (same scheme as the step kernels, drone_device.cuh)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -28,6 +32,8 @@ __global__ void __launch_bounds__(kRedBlock) moments_kernel(const float* __restr
 {
     __shared__ double s_s[kRedBlock / 32], s_q[kRedBlock / 32];
     double s = 0.0, q = 0.0;
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t tid = (int64_t)blockIdx.x * kRedBlock + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * kRedBlock;
     // leading scalars until x is 16-byte aligned, then float4, then the tail
@@ -35,11 +41,20 @@ __global__ void __launch_bounds__(kRedBlock) moments_kernel(const float* __restr
     if (head > n) head = n;
     const int64_t n4 = (n - head) / 4;
     const float4* x4 = reinterpret_cast<const float4*>(x + head);
-    for (int64_t j = tid; j < n4; j += nthreads) {
-        const float4 v = __ldg(x4 + j);
-        // partial sums of 4 in float would lose bits; go to double per element
-        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-        q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    // four independent 16-byte loads in flight per thread per trip (one load at a time is latency-bound)
+    for (int64_t j = tid; j < n4; j += 4 * nthreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = j + u * nthreads;
+            v[u] = k < n4 ? __ldg(x4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // partial sums of 4 in float would lose bits; go to double per element
+            s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
+            q += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+        }
     }
     if (tid < head) { const double v = x[tid]; s += v; q += v * v; }
     const int64_t tail0 = head + 4 * n4;
@@ -64,6 +79,8 @@ __global__ void __launch_bounds__(kRedBlock) moments_kernel(const float* __restr
 __global__ void __launch_bounds__(kRedBlock) normalize_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                const double* __restrict__ m, double eps, int64_t n)
 {
+    pdl_wait();                                            // the moments (and x) come from the previous kernels
+    pdl_launch_dependents();
     const double cnt = m[0], s = m[1], q = m[2];
     const double mean = cnt > 0 ? s / cnt : 0.0;
     double var = cnt > 1 ? (q - s * mean) / (cnt - 1.0) : 0.0;     // unbiased, torch.std default
@@ -77,10 +94,22 @@ __global__ void __launch_bounds__(kRedBlock) normalize_kernel(const float* __res
         const int64_t n4 = n / 4;
         const float4* x4 = reinterpret_cast<const float4*>(x);
         float4* y4 = reinterpret_cast<float4*>(y);
-        for (int64_t j = tid; j < n4; j += nthreads) {
-            float4 v = __ldg(x4 + j);
-            v.x = (v.x - fmean) * inv; v.y = (v.y - fmean) * inv; v.z = (v.z - fmean) * inv; v.w = (v.w - fmean) * inv;
-            y4[j] = v;
+        for (int64_t j = tid; j < n4; j += 4 * nthreads) {      // four independent loads in flight per thread per trip
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t k = j + u * nthreads;
+                if (k < n4) v[u] = __ldg(x4 + k);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t k = j + u * nthreads;
+                if (k < n4) {
+                    v[u].x = (v[u].x - fmean) * inv; v[u].y = (v[u].y - fmean) * inv;
+                    v[u].z = (v[u].z - fmean) * inv; v[u].w = (v[u].w - fmean) * inv;
+                    y4[k] = v[u];
+                }
+            }
         }
         if (tid < n - 4 * n4) y[4 * n4 + tid] = (x[4 * n4 + tid] - fmean) * inv;
     } else {
@@ -98,84 +127,142 @@ __global__ void __launch_bounds__(kRedBlock) normalize_kernel(const float* __res
 // the launch is bound by DRAM latency / kGaeUnroll instead of DRAM latency per step.
 // Chunks are double-buffered in registers: the loads of chunk c+1 are issued BEFORE chunk c is scanned, so loads
 // stay in flight during the dependent arithmetic and the stores (round 1 issued them only after the scan of the
-// previous chunk: 4.4 TB/s; with the prefetch the kernel is bound by HBM, not by its latency).
+// previous chunk: 4.4 TB/s).  A thread owns V adjacent envs (V = 1, 2, 4): one 4V-byte load per array and step
+// instead of V scalar ones, V independent scan chains per thread.  Measured on B200 at 65,536 envs x 250 steps
+// (profiles/r02_gae_variants.jsonl): V = 2, 16-step chunks, 32-thread CTAs is the best register configuration
+// (a thread then keeps 2 x 16 x 18 B in flight); a cp.async shared-memory ring with 4-6 stages per 64-env CTA
+// was tried and is SLOWER (47 us against 39.5: at this size the kernel is a ~33 us stream plus a fixed ~4 us
+// of launch ramp and drain; at 262,144 envs the same kernel runs at 89 % of the measured HBM bandwidth).
+// The launches carry the programmatic-dependent-launch attribute: the CTAs become resident while the previous
+// kernel of the stream drains and wait (griddepcontrol.wait) before their first global access.
+// MOM: the advantage moments (n, sum, sum of squares; K4) are accumulated in the same pass -- the normalisation
+// that follows (Actor_Critic_PPO.ipynb c21:L105) then needs no separate read of the advantage buffer.
 #ifndef DD_GAE_BLOCK
-#define DD_GAE_BLOCK 64
+#define DD_GAE_BLOCK 32
 #endif
 #ifndef DD_GAE_UNROLL
-#define DD_GAE_UNROLL 10
+#define DD_GAE_UNROLL 16
+#endif
+#ifndef DD_GAE_VEC
+#define DD_GAE_VEC 2
 #endif
 constexpr int kGaeBlock = DD_GAE_BLOCK;
 constexpr int kGaeUnroll = DD_GAE_UNROLL;
+constexpr int kGaeVec = DD_GAE_VEC;
 
+template <int V> struct VecLd;
+template <> struct VecLd<1> {
+    static __device__ __forceinline__ void f(const float* p, float (&o)[1]) { o[0] = __ldg(p); }
+    static __device__ __forceinline__ void b(const uint8_t* p, uint8_t (&o)[1]) { o[0] = __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+template <> struct VecLd<2> {
+    static __device__ __forceinline__ void f(const float* p, float (&o)[2]) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1] = t.y; }
+    static __device__ __forceinline__ void b(const uint8_t* p, uint8_t (&o)[2]) { const uchar2 t = __ldg(reinterpret_cast<const uchar2*>(p)); o[0] = t.x; o[1] = t.y; }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <> struct VecLd<4> {
+    static __device__ __forceinline__ void f(const float* p, float (&o)[4]) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+    static __device__ __forceinline__ void b(const uint8_t* p, uint8_t (&o)[4]) { const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+template <int V, int U>
 struct GaeChunk {
-    float r[kGaeUnroll], v[kGaeUnroll];
-    uint8_t d[kGaeUnroll];
-    // steps t1-1 ... t1-kGaeUnroll (clamped at 0: the surplus loads of the last chunk re-read row 0)
+    float r[U][V], v[U][V];
+    uint8_t d[U][V];
+    // steps t1-1 ... t1-U (clamped at 0: the surplus loads of the last chunk re-read row 0)
     __device__ __forceinline__ void load(const float* __restrict__ rew, const float* __restrict__ val,
                                          const uint8_t* __restrict__ done, int32_t t1, int64_t n, int64_t i) {
 #pragma unroll
-        for (int j = 0; j < kGaeUnroll; ++j) {
+        for (int j = 0; j < U; ++j) {
             const int32_t t = t1 - 1 - j;
             const int64_t o = (int64_t)(t >= 0 ? t : 0) * n + i;
-            r[j] = __ldg(rew + o); v[j] = __ldg(val + o); d[j] = __ldg(done + o);
+            VecLd<V>::f(rew + o, r[j]); VecLd<V>::f(val + o, v[j]); VecLd<V>::b(done + o, d[j]);
         }
     }
+    template <bool MOM>
     __device__ __forceinline__ void scan(float* __restrict__ adv, float* __restrict__ ret, float g, float gl, int32_t t1,
-                                         int64_t n, int64_t i, float& gae, float& v_next) const {
+                                         int64_t n, int64_t i, float (&gae)[V], float (&v_next)[V], double& s, double& q) const {
 #pragma unroll
-        for (int j = 0; j < kGaeUnroll; ++j) {
+        for (int j = 0; j < U; ++j) {
             const int32_t t = t1 - 1 - j;
             if (t >= 0) {
                 const int64_t o = (int64_t)t * n + i;
-                const float mask = d[j] ? 0.0f : 1.0f;
-                const float delta = __fsub_rn(__fadd_rn(r[j], __fmul_rn(__fmul_rn(g, v_next), mask)), v[j]);
-                gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, mask), gae));
-                adv[o] = gae;
-                if (ret) ret[o] = __fadd_rn(gae, v[j]);
-                v_next = v[j];
+                float a[V], rt[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const float mask = d[j][e] ? 0.0f : 1.0f;
+                    const float delta = __fsub_rn(__fadd_rn(r[j][e], __fmul_rn(__fmul_rn(g, v_next[e]), mask)), v[j][e]);
+                    gae[e] = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, mask), gae[e]));
+                    a[e] = gae[e];
+                    rt[e] = __fadd_rn(gae[e], v[j][e]);
+                    v_next[e] = v[j][e];
+                    if (MOM) { const double x = (double)gae[e]; s += x; q = fma(x, x, q); }
+                }
+                VecLd<V>::st(adv + o, a);
+                if (ret) VecLd<V>::st(ret + o, rt);
             }
         }
     }
 };
 
+template <int V, bool MOM>
 __global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
                                                         const uint8_t* __restrict__ done, float* __restrict__ adv,
-                                                        float* __restrict__ ret, float g, float gl, int32_t T, int64_t n)
+                                                        float* __restrict__ ret, double* __restrict__ mom, float g, float gl,
+                                                        int32_t T, int64_t n)
 {
-    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
-    if (i >= n) return;
-    float gae = 0.0f;
-    float v_next = __ldg(val + (int64_t)T * n + i);
-    GaeChunk a, b;
-    a.load(rew, val, done, T, n, i);
-    for (int32_t t1 = T; t1 > 0; t1 -= 2 * kGaeUnroll) {       // two chunks per trip: a = [t1-U, t1), b = [t1-2U, t1-U)
-        if (t1 - kGaeUnroll > 0) b.load(rew, val, done, t1 - kGaeUnroll, n, i);
-        a.scan(adv, ret, g, gl, t1, n, i, gae, v_next);
-        if (t1 - kGaeUnroll <= 0) break;
-        if (t1 - 2 * kGaeUnroll > 0) a.load(rew, val, done, t1 - 2 * kGaeUnroll, n, i);
-        b.scan(adv, ret, g, gl, t1 - kGaeUnroll, n, i, gae, v_next);
+    const int64_t i = ((int64_t)blockIdx.x * kGaeBlock + threadIdx.x) * V;
+    double s = 0.0, q = 0.0;
+    pdl_wait();                                            // inputs may come from the previous kernel of the stream
+    pdl_launch_dependents();
+    if (i < n) {
+        float gae[V], v_next[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) gae[e] = 0.0f;
+        VecLd<V>::f(val + (int64_t)T * n + i, v_next);
+        constexpr int U = V == 4 ? (kGaeUnroll + 1) / 2 : kGaeUnroll;     // 2 x U x 9V bytes of registers per thread
+        GaeChunk<V, U> a, b;
+        a.load(rew, val, done, T, n, i);
+        for (int32_t t1 = T; t1 > 0; t1 -= 2 * U) {                // two chunks per trip: a = [t1-U, t1), b = [t1-2U, t1-U)
+            if (t1 - U > 0) b.load(rew, val, done, t1 - U, n, i);
+            a.template scan<MOM>(adv, ret, g, gl, t1, n, i, gae, v_next, s, q);
+            if (t1 - U <= 0) break;
+            if (t1 - 2 * U > 0) a.load(rew, val, done, t1 - 2 * U, n, i);
+            b.template scan<MOM>(adv, ret, g, gl, t1 - U, n, i, gae, v_next, s, q);
+        }
+    }
+    if (MOM) {                                             // block-level sums, one atomic pair per CTA
+        __shared__ double s_s[kGaeBlock / 32 > 0 ? kGaeBlock / 32 : 1], s_q[kGaeBlock / 32 > 0 ? kGaeBlock / 32 : 1];
+        s = warp_sum_d(s); q = warp_sum_d(q);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) { s_s[w] = s; s_q[w] = q; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ts = 0.0, tq = 0.0;
+            for (int k = 0; k < kGaeBlock / 32; ++k) { ts += s_s[k]; tq += s_q[k]; }
+            atomicAdd(mom + 1, ts); atomicAdd(mom + 2, tq);
+            if (blockIdx.x == 0) atomicAdd(mom + 0, (double)T * (double)n);
+        }
     }
 }
 
 // compute_returns (Policy_Gradients.ipynb: G = r + gamma * G over reversed(rewards), python floats = float64),
 // batched: G restarts after a step that ended an episode.  Accumulated in double like the original, written as
-// fp32 (the notebook builds a float32 tensor from the list).  Same chunked load scheme as gae_kernel.
-__global__ void __launch_bounds__(kGaeBlock) returns_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
-                                                            float* __restrict__ out, double gamma, int32_t T, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
-    if (i >= n) return;
-    double G = 0.0;
-    for (int32_t t1 = T; t1 > 0; t1 -= kGaeUnroll) {
-        float r[kGaeUnroll];
-        uint8_t d[kGaeUnroll];
+// fp32 (the notebook builds a float32 tensor from the list).  Same double-buffered chunk scheme as gae_kernel.
+struct RetChunk {
+    float r[kGaeUnroll];
+    uint8_t d[kGaeUnroll];
+    __device__ __forceinline__ void load(const float* __restrict__ rew, const uint8_t* __restrict__ done, int32_t t1, int64_t n, int64_t i) {
 #pragma unroll
         for (int j = 0; j < kGaeUnroll; ++j) {
             const int32_t t = t1 - 1 - j;
             const int64_t o = (int64_t)(t >= 0 ? t : 0) * n + i;
             r[j] = __ldg(rew + o); d[j] = done ? __ldg(done + o) : (uint8_t)0;
         }
+    }
+    __device__ __forceinline__ void scan(float* __restrict__ out, double gamma, int32_t t1, int64_t n, int64_t i, double& G) const {
 #pragma unroll
         for (int j = 0; j < kGaeUnroll; ++j) {
             const int32_t t = t1 - 1 - j;
@@ -186,6 +273,38 @@ __global__ void __launch_bounds__(kGaeBlock) returns_kernel(const float* __restr
             }
         }
     }
+};
+
+__global__ void __launch_bounds__(kGaeBlock) returns_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                            float* __restrict__ out, double gamma, int32_t T, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * kGaeBlock + threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
+    if (i >= n) return;
+    double G = 0.0;
+    RetChunk a, b;
+    a.load(rew, done, T, n, i);
+    for (int32_t t1 = T; t1 > 0; t1 -= 2 * kGaeUnroll) {
+        if (t1 - kGaeUnroll > 0) b.load(rew, done, t1 - kGaeUnroll, n, i);
+        a.scan(out, gamma, t1, n, i, G);
+        if (t1 - kGaeUnroll <= 0) break;
+        if (t1 - 2 * kGaeUnroll > 0) a.load(rew, done, t1 - 2 * kGaeUnroll, n, i);
+        b.scan(out, gamma, t1 - kGaeUnroll, n, i, G);
+    }
+}
+
+// One launch as a programmatic dependent of the previous kernel in the stream.
+template <typename... KP, typename... AP>
+static int launch_pdl(void (*kern)(KP...), int grid, int block, cudaStream_t st, AP... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 static inline int wave_grid(int64_t work_items, int per_block, int max_waves_ctas)
@@ -209,8 +328,7 @@ int dd_moments(const float* x, int64_t n, double* out, void* stream)
     const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 4, dd::kSMs * 8);
     dd::DeviceGuard guard((cudaStream_t)stream, x);
     if (guard.err != cudaSuccess) return (int)guard.err;
-    dd::moments_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(x, n, out);
-    return (int)cudaGetLastError();
+    return dd::launch_pdl(dd::moments_kernel, grid, dd::kRedBlock, (cudaStream_t)stream, x, n, out);
 }
 
 int dd_normalize(const float* x, float* y, const double* moments, double eps, int64_t n, void* stream)
@@ -221,22 +339,38 @@ int dd_normalize(const float* x, float* y, const double* moments, double eps, in
     const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 2, dd::kSMs * 8);
     dd::DeviceGuard guard((cudaStream_t)stream, x);
     if (guard.err != cudaSuccess) return (int)guard.err;
-    dd::normalize_kernel<<<grid, dd::kRedBlock, 0, (cudaStream_t)stream>>>(x, y, moments, eps, n);
-    return (int)cudaGetLastError();
+    return dd::launch_pdl(dd::normalize_kernel, grid, dd::kRedBlock, (cudaStream_t)stream, x, y, moments, eps, n);
+}
+
+int dd_gae_moments(const float* rewards_tn, const float* values_t1n, const uint8_t* dones_tn, float* adv_tn,
+                   float* returns_tn, double* moments, double gamma, double lambda, int32_t T, int64_t n, void* stream)
+{
+    if (!rewards_tn || !values_t1n || !dones_tn || !adv_tn) return DD_E_NULL;
+    if (n < 0 || T < 0) return DD_E_RANGE;
+    if (moments && (reinterpret_cast<uintptr_t>(moments) & 7u)) return DD_E_ALIGN;
+    if (n == 0 || T == 0) return 0;
+    dd::DeviceGuard guard((cudaStream_t)stream, rewards_tn);
+    if (guard.err != cudaSuccess) return (int)guard.err;
+    const float g = (float)gamma, gl = (float)(gamma * lambda);
+    cudaStream_t st = (cudaStream_t)stream;
+    // V envs per thread need every row (stride n elements) of every array aligned to the vector width
+    const uintptr_t fl = reinterpret_cast<uintptr_t>(rewards_tn) | reinterpret_cast<uintptr_t>(values_t1n) |
+                         reinterpret_cast<uintptr_t>(adv_tn) | (returns_tn ? reinterpret_cast<uintptr_t>(returns_tn) : 0);
+    int V = dd::kGaeVec;
+    while (V > 1 && ((n % V) != 0 || (fl & (4u * V - 1)) != 0 || (reinterpret_cast<uintptr_t>(dones_tn) & (V - 1)) != 0)) V >>= 1;
+    const int64_t threads = (n + V - 1) / V;
+    const int grid = (int)((threads + dd::kGaeBlock - 1) / dd::kGaeBlock);
+    double* const no_mom = nullptr;
+#define DD_GAE_LAUNCH(V_) (moments ? dd::launch_pdl(dd::gae_kernel<V_, true>, grid, dd::kGaeBlock, st, rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn, moments, g, gl, T, n) \
+                                   : dd::launch_pdl(dd::gae_kernel<V_, false>, grid, dd::kGaeBlock, st, rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn, no_mom, g, gl, T, n))
+    return V == 4 ? DD_GAE_LAUNCH(4) : (V == 2 ? DD_GAE_LAUNCH(2) : DD_GAE_LAUNCH(1));
+#undef DD_GAE_LAUNCH
 }
 
 int dd_gae(const float* rewards_tn, const float* values_t1n, const uint8_t* dones_tn, float* adv_tn,
            float* returns_tn, double gamma, double lambda, int32_t T, int64_t n, void* stream)
 {
-    if (!rewards_tn || !values_t1n || !dones_tn || !adv_tn) return DD_E_NULL;
-    if (n < 0 || T < 0) return DD_E_RANGE;
-    if (n == 0 || T == 0) return 0;
-    const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
-    dd::DeviceGuard guard((cudaStream_t)stream, rewards_tn);
-    if (guard.err != cudaSuccess) return (int)guard.err;
-    dd::gae_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn,
-                                                                       (float)gamma, (float)(gamma * lambda), T, n);
-    return (int)cudaGetLastError();
+    return dd_gae_moments(rewards_tn, values_t1n, dones_tn, adv_tn, returns_tn, nullptr, gamma, lambda, T, n, stream);
 }
 
 int dd_discounted_returns(const float* rewards_tn, const uint8_t* dones_tn, float* returns_tn, double gamma,
@@ -248,8 +382,7 @@ int dd_discounted_returns(const float* rewards_tn, const uint8_t* dones_tn, floa
     const int grid = (int)((n + dd::kGaeBlock - 1) / dd::kGaeBlock);
     dd::DeviceGuard guard((cudaStream_t)stream, rewards_tn);
     if (guard.err != cudaSuccess) return (int)guard.err;
-    dd::returns_kernel<<<grid, dd::kGaeBlock, 0, (cudaStream_t)stream>>>(rewards_tn, dones_tn, returns_tn, gamma, T, n);
-    return (int)cudaGetLastError();
+    return dd::launch_pdl(dd::returns_kernel, grid, dd::kGaeBlock, (cudaStream_t)stream, rewards_tn, dones_tn, returns_tn, gamma, T, n);
 }
 
 }  // extern "C"

@@ -269,8 +269,7 @@ class BatchedDroneEnv:
             (self.obs.data_ptr() if obs is None else obs) if want_obs else None, self.obs_stride,
             self.reward.data_ptr() if reward is None else reward, self.step_flags.data_ptr() if flags is None else flags,
             _ptr(self.final_obs), self.stats_slots.data_ptr() if stats else None, self.num_envs, C.byref(plan)), "dd_step_plan")
-        ref = C.byref(plan)
-        ref._plan = plan                                   # the byref object keeps the storage alive
+        ref = C.pointer(plan)                              # a ctypes pointer object keeps the storage alive
         self._plans[(want_obs, stats) if key is None else key] = ref
         return ref
 
@@ -422,9 +421,10 @@ class BatchedDroneEnv:
         return {"actions": torch.zeros(n, dtype=torch.uint8, pin_memory=True), "block": block,
                 "obs": obs, "reward": reward, "flags": flags}
 
-    def step_host(self, io, mode: str = "copy") -> None:
-        """HOST in / HOST out step: copies ``io['actions']`` (pinned, packed uint8) to the device, steps, and
-        returns with obs / reward / flags of the step in ``io`` (pinned host memory).
+    def step_host(self, io, mode: str = "copy", actions: Optional[torch.Tensor] = None) -> None:
+        """HOST in / HOST out step: copies ``actions`` (pinned host memory, packed uint8 [N]; default
+        ``io['actions']``) to the device, steps, and returns with obs / reward / flags of the step in ``io``
+        (pinned host memory).
 
         ``mode='copy'``      the kernel writes its packed output block in HBM, ONE device->host copy brings it back
                              (65 B per env-step: this copy is what bounds the call, PCIe);
@@ -432,7 +432,7 @@ class BatchedDroneEnv:
                              under UVA): the observation tile of each CTA leaves the SM as one TMA bulk store straight
                              over PCIe, there is no HBM round trip and no separate copy."""
         stream = torch.cuda.current_stream(self.device)
-        self._packed.copy_(io["actions"], non_blocking=True)
+        self._packed.copy_(io["actions"] if actions is None else actions, non_blocking=True)
         if mode == "copy":
             self.step_raw(self._packed)
             io["block"].copy_(self._out_block, non_blocking=True)

@@ -18,7 +18,8 @@ import torch
 from . import _native as nv
 from .env import BatchedDroneEnv
 
-BLOB_BYTES = 66832
+BLOB_BYTES = 65568
+_OPERANDS = {"auto": nv.OPERANDS_AUTO, "bf16": nv.OPERANDS_BF16, "fp16": nv.OPERANDS_FP16}
 ACTION_THRESHOLD, ACTION_SAMPLE = 0, 1
 _KEYS = ("network.0.weight", "network.0.bias", "network.1.weight", "network.1.bias",
          "network.3.weight", "network.3.bias", "network.4.weight", "network.4.bias",
@@ -29,16 +30,18 @@ _SHAPES = ((128, 15), (128,), (128,), (128,), (128, 128), (128,), (128,), (128,)
 
 
 class PolicyBlob:
-    """Device-resident packed network (66,832 bytes) + its host-side per-column constants.
+    """Device-resident packed network (65,568 bytes) + its host-side per-column constants.
     ``head=3``: the policy ``DroneGamerBoi`` (sigmoid probabilities); ``head=1``: the critic
     ``DroneTeacherBoi`` (same trunk, ``Linear(64, 1)``, raw scalar) -- see ``ValueBlob``."""
 
-    def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda", head: int = 3):
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda", head: int = 3, operands: str = "auto"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PolicyBlob lives on a CUDA device")
         if head not in (1, 3):
             raise ValueError("head must be 3 (policy) or 1 (critic)")
+        if operands not in _OPERANDS:
+            raise ValueError("operands must be 'auto', 'bf16' or 'fp16'")
         self.head = head
         shapes = _SHAPES[:-2] + ((head, 64), (head,))
         params = []
@@ -65,20 +68,21 @@ class PolicyBlob:
         self.blob = torch.empty(BLOB_BYTES, dtype=torch.uint8, device=self.device)
         self.consts = nv.DDPolicyConsts()                  # host side: rides in the kernel-argument constant bank
         pol = nv.DDPolicy(*[t.data_ptr() for t in params])
-        with torch.cuda.device(self.device):
-            pack = nv.lib().dd_policy_pack if head == 3 else nv.lib().dd_value_pack
-            nv.check(pack(C.byref(pol), self.blob.data_ptr(), C.byref(self.consts),
-                          torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack" if head == 3 else "dd_value_pack")
+        # 'auto': fp16 operand images when the network provably fits the fp16 range (checked on the device from the
+        # parameters, include/drone_b200.h DD_OPERANDS_*), else bf16; 'fp16' raises when it does not fit
+        nv.check(nv.lib().dd_policy_pack_ex(C.byref(pol), head, _OPERANDS[operands], self.blob.data_ptr(), C.byref(self.consts),
+                                            torch.cuda.current_stream(self.device).cuda_stream), "dd_policy_pack_ex")
+        self.operand_dtype = "fp16" if self.consts.operands == nv.OPERANDS_FP16 else "bf16"
 
     @classmethod
-    def from_module(cls, module: torch.nn.Module, device="cuda", head: int = 3) -> "PolicyBlob":
-        return cls(module.state_dict(), device=device, head=head)
+    def from_module(cls, module: torch.nn.Module, device="cuda", head: int = 3, operands: str = "auto") -> "PolicyBlob":
+        return cls(module.state_dict(), device=device, head=head, operands=operands)
 
 
-def ValueBlob(state_dict: Mapping[str, torch.Tensor], device="cuda") -> PolicyBlob:
+def ValueBlob(state_dict: Mapping[str, torch.Tensor], device="cuda", operands: str = "auto") -> PolicyBlob:
     """The critic ``DroneTeacherBoi`` (Actor_Critic_PPO.ipynb: 15-128-128-64-1, LayerNorm + ReLU) packed for
     ``value_forward``."""
-    return PolicyBlob(state_dict, device=device, head=1)
+    return PolicyBlob(state_dict, device=device, head=1, operands=operands)
 
 
 def _rows(obs: torch.Tensor) -> torch.Tensor:

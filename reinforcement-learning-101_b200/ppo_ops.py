@@ -28,10 +28,12 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma: float = 0.99,
         lambda_: float = 0.95, want_returns: bool = False, out: Optional[torch.Tensor] = None,
-        out_returns: Optional[torch.Tensor] = None):
+        out_returns: Optional[torch.Tensor] = None, moments: Optional[torch.Tensor] = None):
     """``rewards`` fp32 [T,N], ``values`` fp32 [T+1,N] (bootstrap row last), ``dones`` uint8 [T,N]
     (non-zero = episode ended on that step).  Returns advantages [T,N] (and returns = adv + V).
-    ``out`` / ``out_returns``: preallocated fp32 [T,N] result buffers."""
+    ``out`` / ``out_returns``: preallocated fp32 [T,N] result buffers.  ``moments``: float64[3] on the device;
+    the scan ACCUMULATES (n, sum, sum of squares) of the advantages into it in the same pass, so
+    ``normalize_advantages(adv, moments=m)`` needs no separate read of the buffer (zero it per iteration)."""
     _need(rewards, torch.float32, "rewards")
     _need(values, torch.float32, "values")
     _need(dones, torch.uint8, "dones")
@@ -46,9 +48,11 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma:
     adv = torch.empty_like(rewards) if out is None else out
     want_returns = want_returns or out_returns is not None
     ret = (torch.empty_like(rewards) if out_returns is None else out_returns) if want_returns else None
-    nv.check(nv.lib().dd_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), adv.data_ptr(),
-                             None if ret is None else ret.data_ptr(), float(gamma), float(lambda_), T, n,
-                             _stream(rewards)), "dd_gae")
+    if moments is not None and (moments.dtype != torch.float64 or moments.numel() != 3 or moments.device != rewards.device):
+        raise ValueError("moments must be a float64[3] tensor on the rewards' device")
+    nv.check(nv.lib().dd_gae_moments(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), adv.data_ptr(),
+                                     None if ret is None else ret.data_ptr(), None if moments is None else moments.data_ptr(),
+                                     float(gamma), float(lambda_), T, n, _stream(rewards)), "dd_gae_moments")
     return (adv, ret) if want_returns else adv
 
 
@@ -83,9 +87,10 @@ def advantage_moments(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> to
 
 
 def normalize_advantages(x: torch.Tensor, eps: float = 1e-8, reduce: bool = True,
-                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Globally normalised advantages; ``reduce=True`` sums the moments over all ranks first."""
-    m = advantage_moments(x)
+                         out: Optional[torch.Tensor] = None, moments: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Globally normalised advantages; ``reduce=True`` sums the moments over all ranks first.  ``moments``: this
+    rank's (n, sum, sum of squares) when ``gae(..., moments=m)`` already accumulated them (left untouched)."""
+    m = advantage_moments(x) if moments is None else moments.clone()
     if reduce:
         allreduce_moments(m)
     if out is None:

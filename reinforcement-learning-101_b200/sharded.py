@@ -16,9 +16,11 @@ c16:L42-108), for both kinds of caller:
     chains, one graph replay.
   * ``run(k)`` -- actions from a device-resident trace (BASELINE.json configs[1] "fixed action trace", configs[2]
     "synthetic random actions"): launch j of the env's life (``self.t`` counts them) steps shard ``j % S`` with trace
-    row ``(j // S) % L``.  The schedule has period ``S * L`` launches; ``run`` cuts its k launches at period
-    boundaries and replays one cached graph per distinct (offset, length) piece, so ANY k -- 20 or 12,000 -- runs
-    from graphs and the result is bit-identical to stepping the shards eagerly in that order (tested).
+    row ``(j // S) % L``.  The schedule has period ``S * L`` launches; a call's k launches are one piece (or pieces of
+    one period each), a piece is identified by (offset in the period, length) and replays cached graphs -- one per
+    chain -- so ANY k, 20 or 12,000, runs from graphs, and the result is bit-identical to stepping the shards eagerly
+    in that order (tested).  ``run`` / ``step_all`` return as soon as the work is enqueued on the env's own chain
+    streams; ``join()`` orders the caller's stream behind it.
 
 Global env ids are contiguous over the shards (``env_id_base + s * N + i``), so a ShardedDroneEnv of S x N envs is the
 same set of trajectories as one BatchedDroneEnv of S * N envs (Philox is keyed by the global id).
@@ -60,9 +62,11 @@ class ShardedDroneEnv:
         self._graphs: "OrderedDict[tuple, torch.cuda.CUDAGraph]" = OrderedDict()
         self.graph_replays = 0
         self.eager_launches = 0
+        self._dirty = False                                     # chain streams hold work the caller's stream has not joined
 
     # ---- set-up -------------------------------------------------------------------------------------------
     def reset(self, want_obs: bool = True) -> None:
+        self.join()
         for e in self.shards:
             e.reset(want_obs=want_obs)
         self.t = 0
@@ -72,6 +76,7 @@ class ShardedDroneEnv:
         what launch j of ``run`` reads.  Replaces the trace and drops the graphs captured over the old one."""
         if trace.dtype != torch.uint8 or tuple(trace.shape) != (self.L, self.S, self.N) or trace.device != self.device:
             raise ValueError(f"trace must be a uint8 tensor of shape {(self.L, self.S, self.N)} on {self.device}")
+        self.join()
         self.trace = trace.contiguous()
         self._drop_graphs("run")
 
@@ -85,53 +90,74 @@ class ShardedDroneEnv:
         return tr
 
     # ---- the launch schedule -------------------------------------------------------------------------------
-    def _emit(self, jobs, want_obs: bool) -> None:
-        """Enqueue ``jobs`` = [(shard, actions uint8[N]) ...] in order, shard s on chain s % C, forked from and joined
-        back into the current stream.  Works the same eagerly and under stream capture."""
+    # Shard s lives on chain stream s % C for its whole life, so each shard's launches are stream-ordered whatever
+    # piece / graph they come from.  A piece of the schedule is ONE CUDA GRAPH PER CHAIN (that chain's launches of the
+    # piece, back to back, programmatic dependent launch between them); the chains are never joined to each other --
+    # only to the caller's stream: forked from it when a piece is enqueued (cheap: an event), joined back by join().
+    # A join per piece would drain both chains at every graph boundary: ~1 us per step at 20-launch pieces (measured).
+    def _fork(self) -> None:
         cur = torch.cuda.current_stream(self.device)
-        used = sorted({s % self.C for s, _ in jobs})
-        for c in used:
-            self._chains[c].wait_stream(cur)
+        for ch in self._chains:
+            ch.wait_stream(cur)
+        self._dirty = True
+
+    def join(self) -> None:
+        """Make the caller's current stream wait for everything this env has enqueued on its chain streams.  Called by
+        every method of this class that hands tensors back; call it yourself before touching ``shards[s]`` buffers
+        (``.obs``, ``.reward`` ...) or calling ``shards[s]`` methods directly after ``run`` / ``step_all``."""
+        if self._dirty:
+            cur = torch.cuda.current_stream(self.device)
+            for ch in self._chains:
+                cur.wait_stream(ch)
+            self._dirty = False
+
+    def _emit_chain(self, c: int, jobs, want_obs: bool) -> None:
+        """Enqueue chain c's part of ``jobs`` = [(shard, actions uint8[N]) ...] on the CURRENT stream, in order."""
         for s, act in jobs:
-            with torch.cuda.stream(self._chains[s % self.C]):
+            if s % self.C == c:
                 self.shards[s].step_raw(act, want_obs=want_obs)
-        for c in used:
-            cur.wait_stream(self._chains[c])
 
     def _play(self, key: tuple, make_jobs, want_obs: bool) -> None:
         """``make_jobs()`` builds the job list; it is only called when the piece is not in the graph cache."""
+        self._fork()
         if not self.use_graphs:
             jobs = make_jobs()
-            self._emit(jobs, want_obs)
+            for c in range(self.C):
+                with torch.cuda.stream(self._chains[c]):
+                    self._emit_chain(c, jobs, want_obs)
             self.eager_launches += len(jobs)
             return
-        g = self._graphs.get(key)
-        if g is None:
-            g = self._capture(make_jobs(), want_obs)
-            self._graphs[key] = g
+        gs = self._graphs.get(key)
+        if gs is None:
+            gs = self._capture(make_jobs(), want_obs)
+            self._graphs[key] = gs
             while len(self._graphs) > self.max_graphs:
                 self._graphs.popitem(last=False)
         else:
             self._graphs.move_to_end(key)
-        g.replay()
-        self.graph_replays += 1
+        for c, g in enumerate(gs):
+            if g is not None:
+                with torch.cuda.stream(self._chains[c]):
+                    g.replay()
+                self.graph_replays += 1
 
-    def _capture(self, jobs, want_obs: bool) -> torch.cuda.CUDAGraph:
+    def _capture(self, jobs, want_obs: bool):
         for s in {s for s, _ in jobs}:                      # resolve the step plans outside the capture
             e = self.shards[s]
             if e._needs_reset:
                 raise RuntimeError("call reset() before stepping")
             if (want_obs, True) not in e._plans:
                 e._make_plan(want_obs, True)
-        g = torch.cuda.CUDAGraph()
-        cur = torch.cuda.current_stream(self.device)
-        side = torch.cuda.Stream(self.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(g, stream=side):
-                self._emit(jobs, want_obs)
-        cur.wait_stream(side)
-        return g
+        gs = []
+        for c in range(self.C):
+            if not any(s % self.C == c for s, _ in jobs):
+                gs.append(None)
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._chains[c]):
+                self._emit_chain(c, jobs, want_obs)
+            gs.append(g)
+        return gs
 
     def _drop_graphs(self, kind: str) -> None:
         for k in [k for k in self._graphs if k[0] == kind]:
@@ -146,9 +172,10 @@ class ShardedDroneEnv:
         period = self.S * self.L
         while k > 0:
             off = self.t % period
-            seg = min(k, period - off)
+            seg = min(k, period)                            # a piece may wrap around the period: rows are taken mod L
             self._play(("run", off, seg, want_obs),
-                       lambda: [((off + j) % self.S, self.trace[(off + j) // self.S, (off + j) % self.S]) for j in range(seg)],
+                       lambda: [((off + j) % self.S, self.trace[((off + j) // self.S) % self.L, (off + j) % self.S])
+                                for j in range(seg)],
                        want_obs)
             self.t += seg
             k -= seg
@@ -162,6 +189,7 @@ class ShardedDroneEnv:
                 raise ValueError(f"actions must be uint8 of shape {(self.S, self.N)}")
             self.actions.copy_(actions, non_blocking=True)
         self._play(("all", want_obs), lambda: [(s, self.actions[s]) for s in range(self.S)], want_obs)
+        self.join()
         return ([e.obs for e in self.shards], [e.reward for e in self.shards], [e.step_flags for e in self.shards])
 
     @property
@@ -171,18 +199,21 @@ class ShardedDroneEnv:
     @max_steps.setter
     def max_steps(self, v: Optional[int]) -> None:
         """Curriculum knob for every shard; the captured graphs embed the old value and are dropped."""
+        self.join()
         for e in self.shards:
             e.max_steps = v
         self._graphs.clear()
 
     # ---- statistics / state -------------------------------------------------------------------------------------
     def stats_tensor(self) -> torch.Tensor:
+        self.join()
         out = self.shards[0].stats_tensor().clone()
         for e in self.shards[1:]:
             out += e.stats_tensor()
         return out
 
     def reset_stats(self) -> None:
+        self.join()
         for e in self.shards:
             e.reset_stats()
 

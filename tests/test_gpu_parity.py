@@ -8,9 +8,12 @@ Tolerances (north_star):
     rewards (rtol 1e-5 + atol 1e-5; SURVEY.md 7 hard-part 1), flags / counters bit-exact EXCEPT
     for envs whose float64 state lies within ``BAND`` of a termination threshold on the step
     where the decision differs; those are listed, bounded in number, and compared only up to
-    that step.  BAND is 2e-3 px (or deg, px/step): north_star's literal 1e-6 band is smaller
+    that step.  BAND is 2e-4 px (or deg, px/step): north_star's literal 1e-6 band is smaller
     than the accumulated fp32 position error (~1.7e-3 px after 250 steps) and cannot be met by
-    any fp32 state; the observed flip rate is a few 1e-4 per episode.
+    any fp32 state (the float64 instantiation is the path that meets it: bit-exact); observed on
+    B200: one flip per run, with float64 margins 1.9e-5 / 4.1e-5 px -- a flip rate of a few 1e-5
+    per episode.  The same bound holds for the HOST instantiation of the same source
+    (tests/test_host_twin_cpu.py).
 """
 import importlib
 import json
@@ -35,7 +38,7 @@ def _eq(a, b):
 dd = importlib.import_module("reinforcement-learning-101_b200")
 nv = dd.native
 
-BAND = 2e-3
+BAND = 2e-4
 OBS_NAMES = ("drone_x", "drone_y", "drone_vx", "drone_vy", "drone_angle", "drone_angular_vel", "drone_fuel",
              "platform_x", "platform_y", "distance_to_platform", "dx_to_platform", "dy_to_platform", "speed",
              "landed", "crashed")
@@ -140,7 +143,7 @@ def test_corpus_f32_vs_oracle():
         assert ok.all(), f"step {t}: obs outside fp32 tolerance, max abs err {np.abs(obs - oo)[valid].max():.3g}"
         assert _close32(rew, orr)[valid].all(), f"step {t}: reward outside fp32 tolerance"
         worst = max(worst, float(np.abs(obs - oo)[valid].max()))
-    assert len(flips) <= 8, flips            # ~3e-5..3e-4 per episode expected
+    assert len(flips) <= 2, flips            # ~3e-5 per episode expected (3,650 episodes in the corpus)
     print(f"fp32 corpus: {len(flips)} threshold flips {flips}, worst normalised-obs abs error {worst:.3g}")
 
 
@@ -406,8 +409,9 @@ def test_moments_and_normalize(n):
         np.testing.assert_allclose(y.cpu().numpy(), t64.cpu().numpy(), rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("T,n", [(1, 1), (250, 1000), (33, 4099)])
+@pytest.mark.parametrize("T,n", [(1, 1), (250, 1000), (33, 4099), (251, 4098), (19, 65536), (20, 6)])
 def test_gae_bit_exact(T, n):
+    """n covers every vector width of the scan (n % 4 == 0, n % 2 == 0, odd) and T the chunk tails."""
     rng = np.random.default_rng(T * 1000 + n)
     r = rng.normal(size=(T, n)).astype(np.float32)
     v = rng.normal(size=(T + 1, n)).astype(np.float32)
@@ -416,6 +420,20 @@ def test_gae_bit_exact(T, n):
     ref = co.gae(r, v, d, 0.99, 0.95)
     assert np.array_equal(adv.cpu().numpy(), ref)
     assert np.array_equal(ret.cpu().numpy(), ref + v[:-1])
+    # the moments accumulated in the same pass == dd_moments over the written buffer; unaligned views fall back
+    m = torch.zeros(3, dtype=torch.float64, device="cuda:0")
+    adv2 = dd.gae(_t(r), _t(v), _t(d), 0.99, 0.95, moments=m)
+    assert torch.equal(adv2, adv)
+    m2 = dd.advantage_moments(adv).cpu().numpy()
+    assert m[0].item() == T * n
+    np.testing.assert_allclose(m.cpu().numpy()[1:], m2[1:], rtol=1e-11, atol=1e-8)
+    if n > 1:
+        y1 = dd.normalize_advantages(adv, reduce=False)
+        y2 = dd.normalize_advantages(adv, reduce=False, moments=m)
+        np.testing.assert_allclose(y1.cpu().numpy(), y2.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    big = torch.zeros((T + 1) * n + 1, device="cuda:0")
+    rv = big[1:T * n + 1].view(T, n); rv.copy_(_t(r))                  # 4-byte aligned only
+    assert np.array_equal(dd.gae(rv, _t(v), _t(d), 0.99, 0.95).cpu().numpy(), ref)
     # and the notebook's own loop (Actor_Critic_PPO.ipynb c15:L49-53) in eager torch, one env
     i = n // 2
     rt, vt, dt = torch.tensor(r[:, i]), torch.tensor(v[:, i]), torch.tensor(d[:, i], dtype=torch.float32)
@@ -517,3 +535,86 @@ def test_curriculum_sweep_matches_oracle():
     assert rates == sorted(rates) and rates[-1] > rates[0]      # longer caps let more bang-bang episodes land
     with pytest.raises(ValueError):
         dd.collect_episodes(dd.BatchedDroneEnv(8, device="cuda:0", auto_reset=True), 10)
+
+
+# =================================================================================================
+# round 2: fp32 at size against the float64 oracle, and the device kernel against the HOST
+# instantiation of its own source
+# =================================================================================================
+def test_f32_65536_envs_250_steps_vs_oracle():
+    """BASELINE configs[3]'s population (65,536 envs x 250 steps, auto-reset off so that every env is compared for its
+    whole episode) through the fp32 kernel against the float64 C oracle: north_star's 1e-5 on observations / rewards,
+    flags and counters exact outside the BAND rule, flip rate reported and bounded."""
+    n, T = 65536, 250
+    i = np.arange(n)
+    sx, sy = 100 + (i * 7919) % 601, 50 + (i * 104729) % 201
+    spx, spy = 100 + (i * 1299709) % 600, 100 + (i * 15485863) % 450
+    A = co.random_actions(21, 0, 0, T, n)
+    A[:, 1::2] &= np.where(co.random_actions(22, 0, 0, T, n)[:, 1::2] < 2, 7, 1).astype(np.uint8)   # odd envs: side thrust rarely
+    o = co.OracleBatch(n, randomize_drone=False, randomize_platform=False)
+    o.inject(sx, sy, spx, spy)
+    e = _env(n, dtype=torch.float32)
+    e.inject(_t(sx, torch.float32), _t(sy, torch.float32), _t(spx, torch.float32), _t(spy, torch.float32))
+    Ad = _t(A)
+    valid = np.ones(n, bool)
+    flips, worst = [], 0.0
+    for t in range(T):
+        oo, orr, od = o.step(A[t])
+        obs, rew, fl = e.step_raw(Ad[t])
+        fl = fl.cpu().numpy()
+        bad = valid & (fl != od)
+        if bad.any():
+            margin = _threshold_margin(o)
+            for j in np.nonzero(bad)[0]:
+                assert margin[j] < BAND, f"env {j} step {t}: flags {fl[j]:#x} vs {od[j]:#x}, margin {margin[j]:.3g}"
+                flips.append((int(j), t, float(margin[j])))
+            valid &= ~bad
+        if t % 10 == 9 or t == T - 1:                       # full compare every 10th step (the errors accumulate)
+            assert np.array_equal(e.steps.cpu().numpy()[valid], o.steps[valid])
+            obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+            assert _close32(obs, oo)[valid].all(), f"step {t}: obs outside fp32 tolerance"
+            assert _close32(rew, orr)[valid].all(), f"step {t}: reward outside fp32 tolerance"
+            worst = max(worst, float(np.abs(obs - oo)[valid].max()))
+    episodes = int((o.flags & co.DONE).astype(bool).sum())
+    assert episodes > 0.8 * n
+    assert len(flips) <= 8, flips                           # observed: 1-2 per run (~3e-5 per episode)
+    print(f"fp32 at size: {len(flips)} flips in {episodes} episodes {flips}, worst normalised-obs abs error {worst:.3g}")
+
+
+def test_device_kernel_vs_host_instantiation_of_the_same_source():
+    """One step from identical states: step_kernel<float> on the GPU against csrc/drone_core.cuh instantiated for the
+    host (tests/hosttwin.py).  Everything that does not pass through sin / cos must be BIT-IDENTICAL (same source, same
+    explicit roundings); where sin / cos enter (main thruster fired, or the landing test ran) the two may differ by the
+    device's sincospif rounding: <= 2 ulp of the velocity.  float64: identical up to libm-vs-CUDA sin / cos ulps."""
+    from hosttwin import HostBatch
+    n = 20000
+    kw = dict(seed=31, randomize_drone=True, randomize_platform=True, max_steps=120, auto_reset=True)
+    for dtype, npdt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+        e = dd.BatchedDroneEnv(n, device="cuda:0", dtype=dtype, **kw)
+        e.reset()
+        e.rollout(57, "random")                              # a population of mid-flight states
+        h = HostBatch(n, npdt, **kw)
+        for t in range(3):
+            st = e.get_state()
+            h.pos_vel[:] = e.pos_vel.cpu().numpy(); h.att_fuel[:] = e.att_fuel.cpu().numpy()
+            h.platform[:] = e.platform.cpu().numpy(); h.steps[:] = e.steps.cpu().numpy()
+            h.episode[:] = e.episode.cpu().numpy().astype(np.uint32); h.flags[:] = e.flags.cpu().numpy()
+            act = e.random_actions(1, t0=1000 + t)[0]
+            obs_d, rew_d, fl_d = e.step_raw(act)
+            obs_h, rew_h, fl_h = h.step(act.cpu().numpy())
+            obs_d, rew_d, fl_d = obs_d.cpu().numpy(), rew_d.cpu().numpy(), fl_d.cpu().numpy()
+            a_np = act.cpu().numpy()
+            no_trig = ((a_np & 1) == 0) & (fl_d == 0) & (fl_h == 0)        # main thruster off, still flying
+            assert no_trig.sum() > n // 4
+            if dtype == torch.float32:
+                assert np.array_equal(obs_d[no_trig].view(np.uint32), obs_h[no_trig].view(np.uint32))
+                assert np.array_equal(rew_d[no_trig].view(np.uint32), rew_h[no_trig].view(np.uint32))
+                assert np.array_equal(e.pos_vel.cpu().numpy()[no_trig].view(np.uint32), h.pos_vel[no_trig].view(np.uint32))
+                same = fl_d == fl_h
+                assert (~same).sum() <= 2                                   # a threshold decision on a 1-ulp difference
+                both = same & (fl_d == 0)
+                assert np.abs(obs_d[both].astype(np.float64) - obs_h[both]).max() <= 3e-7    # ~2 ulp of v / 10
+            else:
+                assert np.array_equal(fl_d, fl_h)
+                np.testing.assert_allclose(obs_d, obs_h, rtol=1e-14, atol=1e-15)
+                np.testing.assert_allclose(rew_d, rew_h, rtol=1e-14, atol=1e-15)

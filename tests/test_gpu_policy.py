@@ -1,13 +1,13 @@
 """K5 -- the fused policy rollout (tcgen05 MLP + env step in one kernel) on the GPU.
 
-Tolerances.  The dense layers run on the tensor cores with bf16 operands (LayerNorm centring and gamma
-folded into the weight images by dd_policy_pack; the first layer in split bf16, ~16 mantissa bits) and fp32
-accumulation, so against the notebook's eager fp32 network the logits differ by up to ~2e-2 (measured 0.020
-max on the fixture batch by an emulation of the same roundings in torch): probabilities are compared with
-atol 1e-2, and thresholded actions may only differ where the fp32 |logit| < 0.05.  Against that emulation
-(same roundings, different summation order) the kernel must agree to 3e-3 -- that is the check that the
-UMMA descriptors / layouts / LayerNorm epilogues are right.  The critic (values of magnitude ~250) is
-compared relative to that scale.
+Tolerances.  The dense layers run on the tensor cores with 16-bit operands (LayerNorm centring, sign(gamma) and
+the previous layer's |gamma| folded into the weight images by dd_policy_pack; the first layer in split 16-bit) and
+fp32 accumulation.  The operand format is fp16 when the network provably fits its range (the reference checkpoints
+do), bf16 otherwise.  Against the notebook's eager fp32 network: fp16 -- probabilities within 2e-3 (fixture) / 5e-3
+(all 16.4 M rows of a cfg-4 rollout), thresholded actions differ only where |logit| < 0.02; bf16 -- 1e-2 / |logit| <
+0.05 (round 1's only mode).  Against an emulation of the same roundings in torch (different summation order) the
+kernel must agree to 5e-4 (fp16) / 3e-3 (bf16) -- that is the check that the UMMA descriptors / layouts / LayerNorm
+epilogues are right.  The critic (values of magnitude ~250) is compared in absolute value units.
 The environment half is exact: replaying the actions the fused kernel chose through dd_rollout
 must reproduce rewards, flags and final state bit for bit.
 """
@@ -42,51 +42,57 @@ def fixture(golden_dir):
     return d, sd
 
 
-def _bf(t):
-    return t.to(torch.bfloat16).to(torch.float32)
+def _q(t, f16):
+    """Round to the 16-bit operand format of the blob and back."""
+    return t.to(torch.float16 if f16 else torch.bfloat16).to(torch.float32)
 
 
-def _fold(W, b, g):
-    """dd_policy_pack's operand folding: gamma * (centred over the outputs) weights and bias, and 1/gamma."""
-    gc = torch.where(g.abs() < 1e-12, torch.copysign(torch.full_like(g, 1e-12), g), g)
-    Wc = (W.double() - W.double().mean(0, keepdim=True)).float()
-    bc = (b.double() - b.double().mean()).float()
-    return gc[:, None] * Wc, gc * bc, 1.0 / gc
+def _gabs(g):
+    return g.abs().clamp_min(1e-12)
 
 
-def _hi_lo(v):
-    hi = _bf(v)
-    return hi + _bf(v - hi)
+def _fold(W, b, g, gprev):
+    """dd_policy_pack's operand folding: s (W - column mean over the outputs) g_prev and s (b - mean b), with
+    s = sign(gamma) of THIS layer's LayerNorm and g_prev = |gamma| of the PREVIOUS one (None: the first layer)."""
+    s = torch.where(g < 0, -torch.ones_like(g), torch.ones_like(g))
+    Wc = W - W.double().mean(0, keepdim=True).float()
+    bc = b - b.double().mean().float()
+    img = s[:, None] * Wc
+    if gprev is not None:
+        img = img * _gabs(gprev)[None, :]
+    return img, s * bc
 
 
-def _ln_folded(xpp, ig, be):
-    n = xpp.shape[-1]
-    var = ((xpp * ig) ** 2).sum(-1, keepdim=True) / n
-    return xpp * torch.rsqrt(var + 1e-5) + be
+def _split(t, f16):
+    hi = _q(t, f16)
+    return hi, _q(t - hi, f16)
 
 
-def _split(t):
-    hi = _bf(t)
-    return hi, _bf(t - hi)
+def _ln_folded(xp, beta_over_g):
+    n = xp.shape[-1]
+    var = (xp ** 2).sum(-1, keepdim=True) / n
+    return xp * torch.rsqrt(var + 1e-5) + beta_over_g
 
 
-def _emulate_bf16(sd, x, head=3):
-    """Same operand roundings as the kernel: LayerNorm centring and gamma folded into the weight images;
-    first layer in split bf16 (x_hi W_hi + x_hi W_lo + x_lo W_hi, b0 riding as column 15 against a constant 1);
-    b1/b2 as bf16 hi + lo; bf16 hidden activations and weights, fp32 accumulation, fp32 variance +
-    normalisation, fp32 last layer.  head=3: sigmoid probabilities; head=1: the critic's raw value."""
-    W0, b0, ig0 = _fold(sd["network.0.weight"], sd["network.0.bias"], sd["network.1.weight"])
-    W1, b1, ig1 = _fold(sd["network.3.weight"], sd["network.3.bias"], sd["network.4.weight"])
-    W2, b2, ig2 = _fold(sd["network.6.weight"], sd["network.6.bias"], sd["network.7.weight"])
+def _emulate16(sd, x, head=3, f16=True):
+    """Same operand roundings as the kernel: LayerNorm centring, the sign of gamma and the previous layer's |gamma|
+    folded into the weight images; first layer in split 16-bit (x_hi W_hi + x_hi W_lo + x_lo W_hi, b0 riding as column
+    15 against a constant 1); b1/b2 as hi + lo; 16-bit hidden activations and weights (fp16 or bf16, as the blob says),
+    fp32 accumulation, fp32 variance + normalisation, fp32 last layer (x |gamma| of the last LayerNorm).
+    head=3: sigmoid probabilities; head=1: the critic's raw value."""
+    g0, g1, g2 = sd["network.1.weight"], sd["network.4.weight"], sd["network.7.weight"]
+    W0, b0 = _fold(sd["network.0.weight"], sd["network.0.bias"], g0, None)
+    W1, b1 = _fold(sd["network.3.weight"], sd["network.3.bias"], g1, g0)
+    W2, b2 = _fold(sd["network.6.weight"], sd["network.6.bias"], g2, g1)
     x16 = torch.cat([x, torch.ones(x.shape[0], 1)], 1)
-    (xh, xl), (wh, wl) = _split(x16), _split(torch.cat([W0, b0[:, None]], 1))
+    (xh, xl), (wh, wl) = _split(x16, f16), _split(torch.cat([W0, b0[:, None]], 1), f16)
     h = xh @ wh.T + xh @ wl.T + xl @ wh.T
-    h = torch.relu(_ln_folded(h, ig0, sd["network.1.bias"]))
-    h = _bf(h) @ _bf(W1).T + _hi_lo(b1)
-    h = torch.relu(_ln_folded(h, ig1, sd["network.4.bias"]))
-    h = _bf(h) @ _bf(W2).T + _hi_lo(b2)
-    h = torch.relu(_ln_folded(h, ig2, sd["network.7.bias"]))
-    z = h @ sd["network.9.weight"].T + sd["network.9.bias"]
+    h = torch.relu(_ln_folded(h, sd["network.1.bias"] / _gabs(g0)))
+    h = _q(h, f16) @ _q(W1, f16).T + sum(_split(b1, f16))
+    h = torch.relu(_ln_folded(h, sd["network.4.bias"] / _gabs(g1)))
+    h = _q(h, f16) @ _q(W2, f16).T + sum(_split(b2, f16))
+    h = torch.relu(_ln_folded(h, sd["network.7.bias"] / _gabs(g2)))
+    z = h @ (sd["network.9.weight"] * _gabs(g2)[None, :]).T + sd["network.9.bias"]
     return torch.sigmoid(z) if head == 3 else z.squeeze(-1)
 
 
@@ -95,13 +101,24 @@ def test_forward_matches_torch_on_the_reference_checkpoint(fixture):
     blob = dd.PolicyBlob(sd, device=DEV)
     obs = torch.from_numpy(d["obs"]).to(DEV)
     probs = dd.policy_forward(blob, obs).cpu()
-    emu = _emulate_bf16(sd, torch.from_numpy(d["obs"]))
+    assert blob.operand_dtype == "fp16"                 # the reference checkpoint fits the fp16 range
+    emu = _emulate16(sd, torch.from_numpy(d["obs"]), f16=True)
     ref = torch.from_numpy(d["probs"])
     assert torch.isfinite(probs).all()
-    assert (probs - emu).abs().max().item() < 3e-3, (probs - emu).abs().max().item()
-    assert (probs - ref).abs().max().item() < 1e-2, (probs - ref).abs().max().item()
+    assert (probs - emu).abs().max().item() < 5e-4, (probs - emu).abs().max().item()
+    assert (probs - ref).abs().max().item() < 2e-3, (probs - ref).abs().max().item()
     flips = (probs > 0.5) != (ref > 0.5)
+    assert np.abs(d["logits"])[flips.numpy()].max(initial=0.0) < 0.01
+    # the bf16 images (what a network outside the fp16 range gets) through the same kernels
+    blob_b = dd.PolicyBlob(sd, device=DEV, operands="bf16")
+    assert blob_b.operand_dtype == "bf16"
+    probs_b = dd.policy_forward(blob_b, obs).cpu()
+    assert (probs_b - _emulate16(sd, torch.from_numpy(d["obs"]), f16=False)).abs().max().item() < 3e-3
+    assert (probs_b - ref).abs().max().item() < 1e-2
+    flips = (probs_b > 0.5) != (ref > 0.5)
     assert np.abs(d["logits"])[flips.numpy()].max(initial=0.0) < 0.05
+    print(f"policy fixture: max prob error vs eager fp32: fp16 operands {(probs - ref).abs().max().item():.2e}, "
+          f"bf16 operands {(probs_b - ref).abs().max().item():.2e}")
     # the module-based constructor gives the same blob
     blob2 = dd.PolicyBlob.from_module(reference_policy(sd), device=DEV)
     assert torch.equal(blob.blob, blob2.blob)
@@ -122,11 +139,14 @@ def test_forward_random_weights_ragged_sizes(n):
     blob = dd.PolicyBlob(sd, device=DEV)
     x = torch.randn(n, 15, generator=g)
     probs = dd.policy_forward(blob, x.to(DEV)).cpu()
-    emu = _emulate_bf16(sd, x)
+    f16 = blob.operand_dtype == "fp16"
+    emu = _emulate16(sd, x, f16=f16)
     assert probs.shape == (n, 3)
-    assert (probs - emu).abs().max().item() < 5e-3, (probs - emu).abs().max().item()
+    assert (probs - emu).abs().max().item() < (1e-3 if f16 else 5e-3), (probs - emu).abs().max().item()
     with torch.no_grad():
-        assert (probs - net(x)).abs().max().item() < 8e-2
+        assert (probs - net(x)).abs().max().item() < (1e-2 if f16 else 8e-2)
+    pb = dd.policy_forward(dd.PolicyBlob(sd, device=DEV, operands="bf16"), x.to(DEV)).cpu()
+    assert (pb - _emulate16(sd, x, f16=False)).abs().max().item() < 5e-3
 
 
 def test_forward_degenerate_layernorm_gammas(fixture):
@@ -138,12 +158,15 @@ def test_forward_degenerate_layernorm_gammas(fixture):
         g = sd[key]
         g[0] = 0.0; g[1] = -0.0; g[2] = 1e-20; g[3] = -3e-15; g[4] = -1.7; g[5] = 250.0; g[6] = 1e-6
     blob = dd.PolicyBlob(sd, device=DEV)
+    assert blob.operand_dtype == "bf16"                  # |gamma| < 2^-6: outside the fp16 range -> bf16 images
+    with pytest.raises(nv.NativeError):
+        dd.PolicyBlob(sd, device=DEV, operands="fp16")   # demanding fp16 for it is refused
     x = torch.from_numpy(d["obs"])
     probs = dd.policy_forward(blob, x.to(DEV)).cpu()
     assert torch.isfinite(probs).all()
     with torch.no_grad():
         ref = reference_policy(sd)(x)
-    assert (probs - _emulate_bf16(sd, x)).abs().max().item() < 5e-3
+    assert (probs - _emulate16(sd, x, f16=False)).abs().max().item() < 5e-3
     assert (probs - ref).abs().max().item() < 6e-2
 
 
@@ -276,11 +299,18 @@ def test_critic_value_forward_and_rollout_values(fixture, golden_dir):
     x = torch.from_numpy(c["obs"])
     ref = torch.from_numpy(c["values"])
     v = dd.value_forward(vblob, x.to(DEV)).cpu()
-    emu = _emulate_bf16(sdc, x, head=1)
+    assert vblob.operand_dtype == "fp16"
+    emu = _emulate16(sdc, x, head=1, f16=True)
     scale = ref.std().item()
     assert v.shape == ref.shape and torch.isfinite(v).all()
     assert ((v - emu).abs() / (1 + emu.abs())).max().item() < 2e-3, ((v - emu).abs() / (1 + emu.abs())).max().item()
-    assert (v - ref).abs().max().item() < 0.02 * scale and (v - ref).pow(2).mean().sqrt().item() < 0.003 * scale
+    assert (v - ref).abs().max().item() < 0.4 and (v - ref).pow(2).mean().sqrt().item() < 0.08, \
+        ((v - ref).abs().max().item(), (v - ref).pow(2).mean().sqrt().item())       # absolute, at a value scale of ~254
+    vb = dd.value_forward(dd.ValueBlob(sdc, device=DEV, operands="bf16"), x.to(DEV)).cpu()
+    assert ((vb - _emulate16(sdc, x, head=1, f16=False)).abs() / (1 + emu.abs())).max().item() < 2e-3
+    assert (vb - ref).abs().max().item() < 0.02 * scale
+    print(f"critic fixture: max / rms value error vs eager fp32: fp16 {(v - ref).abs().max().item():.3f} / "
+          f"{(v - ref).pow(2).mean().sqrt().item():.4f}, bf16 {(vb - ref).abs().max().item():.3f} / {(vb - ref).pow(2).mean().sqrt().item():.4f} (value std {scale:.0f})")
     # persistent forward over a rollout buffer: same rows -> same values, whatever the launch shape
     blob = dd.PolicyBlob(sd, device=DEV)
     n, T = 1000, 37
@@ -363,3 +393,54 @@ def test_policy_argument_errors(fixture):
     L = nv.lib()
     assert L.dd_policy_forward(None, None, None, None, 4, None) == -1
     assert L.dd_policy_pack(None, None, None, None) == -1
+
+
+def test_policy_and_critic_against_eager_fp32_on_the_whole_cfg4_buffer(fixture, golden_dir):
+    """the probabilities that drive the actions and the values that feed dd_gae, checked against the
+    notebook's eager fp32 networks (torch on the GPU, test-only) on ALL 16.4 M observation rows of a cfg-4 rollout
+    (65,536 envs x 250 steps), not on a 512-row fixture.  Reported: max / rms error, the thresholded-action flip rate
+    and the largest |logit| at a flip."""
+    d, sd = fixture
+    c = np.load(os.path.join(golden_dir, "critic_v1.npz"))
+    sdc = {k_: torch.from_numpy(c[k_]) for k_ in c.files if k_.startswith("network")}
+    blob, vblob = dd.PolicyBlob(sd, device=DEV), dd.ValueBlob(sdc, device=DEV)
+    n, T = 65536, 250
+    env = dd.BatchedDroneEnv(n, device=DEV, seed=2, randomize_drone=True, randomize_platform=True, max_steps=250,
+                             auto_reset=True, dtype=torch.float32)
+    env.reset()
+    out = dd.policy_rollout(env, blob, T, sample=True, want="op")
+    vals = dd.value_forward(vblob, out["obs"])
+    pol = reference_policy(sd).to(DEV)
+    crit = reference_policy(sdc, head=1).to(DEV)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    rows = out["obs"].view(-1, 15)
+    probs = out["probs"].view(-1, 3)
+    v = vals.view(-1)
+    perr = torch.zeros((), device=DEV); verr = torch.zeros((), device=DEV)
+    psq = torch.zeros((), device=DEV, dtype=torch.float64); vsq = torch.zeros((), device=DEV, dtype=torch.float64)
+    flips = torch.zeros((), device=DEV, dtype=torch.int64); flip_logit = torch.zeros((), device=DEV)
+    vscale_sq = torch.zeros((), device=DEV, dtype=torch.float64)
+    CH = 1 << 20
+    with torch.no_grad():
+        for lo in range(0, rows.shape[0], CH):
+            x = rows[lo:lo + CH]
+            pr = pol(x)
+            dp = (probs[lo:lo + CH] - pr).abs()
+            perr = torch.maximum(perr, dp.max()); psq += dp.double().pow(2).sum()
+            fl = (probs[lo:lo + CH] > 0.5) != (pr > 0.5)
+            flips += fl.sum()
+            logit = torch.log(pr.clamp_min(1e-30)) - torch.log1p(-pr.clamp_max(1 - 1e-7))
+            flip_logit = torch.maximum(flip_logit, (logit.abs() * fl).max())
+            vr = crit(x).squeeze(-1)
+            dv = (v[lo:lo + CH] - vr).abs()
+            verr = torch.maximum(verr, dv.max()); vsq += dv.double().pow(2).sum(); vscale_sq += vr.double().pow(2).sum()
+    m = rows.shape[0]
+    perr, verr, flips, flip_logit = perr.item(), verr.item(), int(flips.item()), flip_logit.item()
+    prms, vrms, vscale = (psq.item() / (3 * m)) ** 0.5, (vsq.item() / m) ** 0.5, (vscale_sq.item() / m) ** 0.5
+    print(f"cfg-4 buffer, {m} rows: probs max err {perr:.2e} rms {prms:.2e}; threshold flips {flips} ({flips / (3 * m):.2e} per action), "
+          f"max |logit| at a flip {flip_logit:.3f}; critic max err {verr:.3f} rms {vrms:.4f} at value rms {vscale:.1f}")
+    assert blob.operand_dtype == "fp16" and vblob.operand_dtype == "fp16"
+    assert perr <= 5e-3, perr                                # (bf16 operands, round 1: 2.4e-2 on this buffer)
+    assert flip_logit < 0.02 and flips / (3 * m) < 5e-4
+    assert verr <= 1.0 and vrms <= 0.1, (verr, vrms)         # absolute, at a value rms of ~250

@@ -111,3 +111,54 @@ def test_shaped_reward_with_auto_reset_and_fused_policy(golden_dir, variant):
     b.rollout(T, "trace", actions=out["actions"], shaped_out=shp_b)
     assert torch.equal(out["shaped"], shp_b)
     assert torch.equal(a.get_state()["prev_dist"].isnan(), b.get_state()["prev_dist"].isnan())
+
+
+@pytest.mark.parametrize("variant", ["ppo", "pg"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_terminal_shaped_rewards_under_auto_reset(dtype, variant):
+    """under auto-reset the observation stream holds the NEXT episode's first observation on a
+    terminal step, so the tests above skip those steps -- but the +800 / -300 / -500 terms on exactly those steps are
+    what PPO learns from.  Here a twin env replays the same actions step by step with want_final_obs=True; its
+    terminal observation rows feed the notebook port, and EVERY step of the rollout is compared."""
+    n, T, ms = 256, 150, 60
+    kw = dict(seed=12, randomize_drone=True, randomize_platform=True, max_steps=ms, auto_reset=True, dtype=dtype, shaping=variant)
+    a = dd.BatchedDroneEnv(n, device=DEV, **kw)
+    obs0 = a.reset().double().cpu().numpy().copy()
+    acts = a.random_actions(T)
+    acts[:, : n // 2] &= 1                                    # half the envs only ever fire the main thruster: some land
+    shp = torch.empty(T, n, dtype=dtype, device=DEV); don = torch.empty(T, n, dtype=torch.uint8, device=DEV)
+    a.rollout(T, "trace", actions=acts, shaped_out=shp, done_out=don)
+    b = dd.BatchedDroneEnv(n, device=DEV, want_final_obs=True, **kw); b.reset()
+    exp = np.zeros((T, n))
+    shapers = [EpisodeShaper(ms, variant=variant) for _ in range(n)]
+    cur = obs0.copy()
+    near = np.zeros((T, n), bool)
+    for t in range(T):
+        obs, rew, flags = b.step_raw(acts[t])
+        obs = obs.double().cpu().numpy(); fin = b.final_obs.double().cpu().numpy(); fl = flags.cpu().numpy()
+        assert np.array_equal(fl, don[t].cpu().numpy())
+        for i in range(n):
+            nxt = fin[i] if fl[i] else obs[i]                 # the state the notebook's calc_reward sees: the terminal one
+            exp[t, i], _ = shapers[i].step(cur[i], nxt)
+            if fl[i]:
+                shapers[i].reset()
+        nxt_all = np.where(fl[:, None] != 0, fin, obs)
+        near[t] = _near_threshold(None, nxt_all)
+        cur = obs                                             # after a reset: the new episode's first observation
+    got = shp.double().cpu().numpy()
+    f = don.cpu().numpy()
+    term = f != 0
+    assert term.sum() > 2 * n
+    if dtype == torch.float64:
+        np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-9)
+    else:
+        bad = np.abs(got - exp) > 2e-3 * np.maximum(1.0, np.abs(exp))
+        assert not (bad & ~near).any(), np.argwhere(bad & ~near)[:5]
+        assert bad.sum() <= 5
+    # the terminal terms themselves
+    landed, crashed, trunc = (f & 2) > 0, (f & 4) > 0, (f & 8) > 0
+    assert crashed.any() and trunc.any()
+    assert (got[crashed] < -150).all()                                  # -200 / -300 (+ -500 when it is also the cap step)
+    assert (got[trunc & ~landed] < -480).all()                          # -500 time-out
+    if landed.any():
+        assert (got[landed] > (790 if variant == "ppo" else 490)).all()  # +800 / +500 + 100 * fuel, never the -500

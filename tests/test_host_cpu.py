@@ -59,14 +59,17 @@ def test_policy_binding_matches_header():
     assert int(re.search(r"#define DD_ENV_RECORD_DOUBLES (\d+)", h).group(1)) == nv.ENV_RECORD_DOUBLES
     body = re.search(r"typedef struct DDPolicyConsts \{(.*?)\} DDPolicyConsts;", h, re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    floats = 0
-    for decl in re.findall(r"float ([^;]+);", body):
+    words = 0
+    for decl in re.findall(r"(?:float|int32_t) ([^;]+);", body):
         for f in decl.split(","):
             n = 1
             for d in re.findall(r"\[(\d+)\]", f):
                 n *= int(d)
-            floats += n
-    assert floats * 4 == C.sizeof(nv.DDPolicyConsts) == 836 * 4
+            words += n
+    assert words * 4 == C.sizeof(nv.DDPolicyConsts) == 520 * 4
+    assert nv.DDPolicyConsts.operands.offset == 516 * 4
+    for name, val in (("DD_OPERANDS_AUTO", nv.OPERANDS_AUTO), ("DD_OPERANDS_BF16", nv.OPERANDS_BF16), ("DD_OPERANDS_FP16", nv.OPERANDS_FP16)):
+        assert int(re.search(rf"#define {name} (\d+)", h).group(1)) == val
     assert C.sizeof(nv.DDPolicy) == 14 * C.sizeof(C.c_void_p)
 
 
