@@ -251,12 +251,26 @@ def run_ours(args):
     import torch.distributed as dist
     dd = importlib.import_module("reinforcement-learning-101_b200")
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
-    rank, local, ws = dd.init_from_env("nccl")
-    if ws != args.gpus and ws > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    # keep stdout to the one JSON line: NCCL prints its version banner to stdout at communicator creation when the
+    # box sets NCCL_DEBUG -- send NCCL's log to stderr and, belt and braces, point fd 1 at stderr while NCCL initialises
+    os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE") or "/dev/stderr"
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local, ws = dd.init_from_env("nccl")
+        if ws != args.gpus and ws > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}")
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if ws > 1:                                             # first collective: the communicator exists after this
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     cpus = dd.bind_to_gpu_numa(local) if ws > 1 and not args.no_numa_bind else None   # host buffers next to the GPU
     K, W, S, n = args.steps, max(args.warmup, 3), args.shards, args.envs
     PK = _peaks_all()
@@ -572,6 +586,31 @@ def run_ours(args):
         ms_e2e = timed(lambda: run_e2e(3), lambda: run_e2e(Ke2))
         launches += Ke2 + 3
         e2e_modes[mode] = ms_e2e / Ke2
+    # the same steps, two in flight: step j+1 (another shard, another pinned buffer, another stream) is enqueued before the
+    # host waits for step j, so the device->host copy of one shard overlaps the host->device copy + kernel of the next.
+    # Every step still takes its actions from pinned host memory and delivers obs / reward / flags to pinned host memory,
+    # and the host waits for every step's results (event) before that buffer is reused.
+    side = [torch.cuda.Stream(dev) for _ in io]
+
+    def run_e2e_pipelined(k):
+        cur = torch.cuda.current_stream(dev)
+        for sd in side:
+            sd.wait_stream(cur)
+        pend = [None] * len(io)
+        for j in range(k):
+            b = j % len(io)
+            if pend[b] is not None:
+                pend[b].synchronize()                        # the host consumes the results of step j - 2 here
+            with torch.cuda.stream(side[b]):
+                pend[b] = shards[j % S].step_host(io[b], mode="copy", actions=host_trace[j % env.L], wait=False)
+        for p_ in pend:
+            if p_ is not None:
+                p_.synchronize()
+        for sd in side:
+            cur.wait_stream(sd)
+    ms_e2e = timed(lambda: run_e2e_pipelined(4), lambda: run_e2e_pipelined(Ke2))
+    launches += Ke2 + 4
+    e2e_modes["copy_2_in_flight"] = ms_e2e / Ke2
     h2d = n * 1
     d2h = n * (shards[0].obs_stride * 4 + 4 + 1)
     # the ceiling of this box for the same bytes: plain cudaMemcpyAsync of the packed block into pinned memory, all
@@ -639,7 +678,11 @@ def run_ours(args):
             },
             "e2e": {"value": n * ws / (ms_e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke2, "ms_per_step": ms_e2e_step,
-                    "api": f"BatchedDroneEnv.step_host(mode='{best_mode}') (pinned host actions in; obs, reward, flags out in pinned host memory)",
+                    "api": {"copy": "BatchedDroneEnv.step_host(mode='copy'): one step at a time, the host waits for each",
+                            "zero_copy": "BatchedDroneEnv.step_host(mode='zero_copy'): the kernel writes straight into pinned host memory",
+                            "copy_2_in_flight": "BatchedDroneEnv.step_host(mode='copy', wait=False) on two streams over independent shards: "
+                                                "two steps in flight, the host waits for every step's event"}[best_mode]
+                           + " (pinned host actions in; obs, reward, flags out in pinned host memory, every step)",
                     "modes_ms_per_step": e2e_modes,
                     "pcie_gbs": (h2d + d2h) / (ms_e2e_step * 1e-3) / 1e9,
                     "pcie_ceiling_gbs": ceil_gbs, "frac_of_pcie_ceiling": (d2h / (ms_e2e_step * 1e-3) / 1e9) / ceil_gbs,
@@ -683,20 +726,23 @@ def multi_gpu_check(dd, dist, cenv, cap, rank, ws, NC, dev):
     (2) advantage moments: normalize_advantages(reduce=True) on per-rank buffers must equal normalising the
         concatenation of all ranks' buffers on one GPU."""
     import torch
-    own = dd.collect_episodes(cenv, cap, policy="bangbang", reduce=False)
-    w_own = cenv.stats_tensor().clone()
+
+    def fresh_stage(base):
+        """One curriculum stage on a FRESH env (episode counters at 0, so the Philox spawn of env id g is the same
+        whichever GPU plays it): returns (stats dict, the 8 device words)."""
+        e = dd.BatchedDroneEnv(NC, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
+                               auto_reset=False, dtype=torch.float32, env_id_base=base)
+        st = dd.collect_episodes(e, cap, policy="bangbang", reduce=False)
+        return st, e.stats_tensor().clone()
+    own, w_own = fresh_stage(rank * NC)
     w_red = dd.allreduce_stats(w_own.clone())
     gathered = [torch.zeros_like(w_own) for _ in range(ws)]
     dist.all_gather(gathered, w_own)
     G = torch.stack(gathered)
     nb = (rank + 1) % ws
-    nenv = dd.BatchedDroneEnv(NC, device=dev, seed=0, randomize_drone=True, randomize_platform=True,
-                              auto_reset=False, dtype=torch.float32, env_id_base=nb * NC)
-    dd.collect_episodes(nenv, cap, policy="bangbang", reduce=False)
-    w_nb = nenv.stats_tensor().clone()
+    _, w_nb = fresh_stage(nb * NC)
     ok_sum = bool(torch.equal(G.sum(0), w_red))
     ok_nb = bool(torch.equal(w_nb, G[nb]))
-    del nenv
     # moments: a deterministic per-rank buffer (the shaped rewards of a short rollout would do; a hash is enough here)
     m = 1 << 18
     idx = torch.arange(m, device=dev, dtype=torch.float32)

@@ -135,12 +135,25 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
+#ifndef DD_K5_WAIT_HINT_NS
+#define DD_K5_WAIT_HINT_NS 0                   // > 0: suspend-time hint of mbarrier.try_wait (the warp sleeps in hardware)
+#endif
+#ifndef DD_K5_ALL_WARPS_WAIT
+#define DD_K5_ALL_WARPS_WAIT 0                 // 1: all four warps of a tile wait on the MMA mbarrier (no second named barrier)
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if DD_K5_WAIT_HINT_NS > 0
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)DD_K5_WAIT_HINT_NS) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // A lost MMA / TMA completion must fault, never hang the GPU -- but the bound is WALL TIME (%globaltimer, 20 s),
@@ -173,9 +186,14 @@ __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1
 // instructions per thread-step when all four warps of a tile poll); the other three block on a second named
 // barrier that the issuing warp joins once the phase has flipped.
 __device__ __forceinline__ void wait_mma(uint32_t bar, uint32_t& phase, bool issuer_warp, int g) {
+#if DD_K5_ALL_WARPS_WAIT
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+#else
     if (issuer_warp) mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("bar.sync %0, %1;" :: "r"(g + 1 + kGroups), "n"(kTile) : "memory");
+#endif
     tc_fence_after();
 }
 

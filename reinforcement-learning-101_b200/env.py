@@ -421,10 +421,13 @@ class BatchedDroneEnv:
         return {"actions": torch.zeros(n, dtype=torch.uint8, pin_memory=True), "block": block,
                 "obs": obs, "reward": reward, "flags": flags}
 
-    def step_host(self, io, mode: str = "copy", actions: Optional[torch.Tensor] = None) -> None:
+    def step_host(self, io, mode: str = "copy", actions: Optional[torch.Tensor] = None, wait: bool = True):
         """HOST in / HOST out step: copies ``actions`` (pinned host memory, packed uint8 [N]; default
         ``io['actions']``) to the device, steps, and returns with obs / reward / flags of the step in ``io``
-        (pinned host memory).
+        (pinned host memory).  ``wait=False`` returns at once with a ``torch.cuda.Event`` instead; ``io`` holds the
+        step's results once ``event.synchronize()`` returns -- a caller that owns several envs (shards) can so keep
+        the device->host copy of one env's step in flight while the next env's actions go up and its kernel runs
+        (call it under ``torch.cuda.stream(...)`` with one stream per env in flight).
 
         ``mode='copy'``      the kernel writes its packed output block in HBM, ONE device->host copy brings it back
                              (65 B per env-step: this copy is what bounds the call, PCIe);
@@ -450,4 +453,9 @@ class BatchedDroneEnv:
             self._prev_dist_stale = True
         else:
             raise ValueError("mode must be 'copy' or 'zero_copy'")
-        stream.synchronize()
+        if wait:
+            stream.synchronize()
+            return None
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev

@@ -90,20 +90,54 @@ def main():
     bits = (g.random((250, n, 3)) < p).astype(np.uint8)
     A2 = (bits[..., 0] | (bits[..., 1] << 1) | (bits[..., 2] << 2)).astype(np.uint8)
     rep["float32_65536_envs_x_250_steps_vs_oracle"] = run(torch.float32, n, 250, sp2, A2)
-    # K5: tensor-core network against the eager fp32 outputs recorded from the reference checkpoints
+    # K5: tensor-core network against the eager fp32 outputs recorded from the reference checkpoints, in both operand
+    # formats (fp16 is what dd_policy_pack picks for these checkpoints; bf16 is the fallback for networks outside its range)
     d = np.load(os.path.join(HERE, "golden", "policy_v1.npz"))
-    blob = dd.PolicyBlob({k: torch.from_numpy(d[k]) for k in d.files if k.startswith("network")}, device=DEV)
-    probs = dd.policy_forward(blob, torch.from_numpy(d["obs"]).to(DEV)).cpu().numpy()
-    flips = (probs > 0.5) != (d["probs"] > 0.5)
-    rep["K5_policy_probs_vs_eager_fp32"] = {"rows": int(d["obs"].shape[0]), "max_abs_err": float(np.abs(probs - d["probs"]).max()),
-                                            "threshold_flips": int(flips.sum()),
-                                            "max_|logit|_at_a_flip": float(np.abs(d["logits"])[flips].max(initial=0.0))}
     c = np.load(os.path.join(HERE, "golden", "critic_v1.npz"))
-    vb = dd.ValueBlob({k: torch.from_numpy(c[k]) for k in c.files if k.startswith("network")}, device=DEV)
-    v = dd.value_forward(vb, torch.from_numpy(c["obs"]).to(DEV)).cpu().numpy()
-    rep["K5_critic_values_vs_eager_fp32"] = {"rows": int(c["obs"].shape[0]), "value_std": float(c["values"].std()),
-                                             "max_abs_err": float(np.abs(v - c["values"]).max()),
-                                             "rms_err": float(np.sqrt(((v - c["values"]) ** 2).mean()))}
+    sd = {k: torch.from_numpy(d[k]) for k in d.files if k.startswith("network")}
+    sdc = {k: torch.from_numpy(c[k]) for k in c.files if k.startswith("network")}
+    for operands in ("fp16", "bf16"):
+        blob = dd.PolicyBlob(sd, device=DEV, operands=operands)
+        probs = dd.policy_forward(blob, torch.from_numpy(d["obs"]).to(DEV)).cpu().numpy()
+        flips = (probs > 0.5) != (d["probs"] > 0.5)
+        rep[f"K5_policy_probs_vs_eager_fp32_{operands}"] = {
+            "rows": int(d["obs"].shape[0]), "max_abs_err": float(np.abs(probs - d["probs"]).max()),
+            "threshold_flips": int(flips.sum()), "max_|logit|_at_a_flip": float(np.abs(d["logits"])[flips].max(initial=0.0))}
+        vb = dd.ValueBlob(sdc, device=DEV, operands=operands)
+        v = dd.value_forward(vb, torch.from_numpy(c["obs"]).to(DEV)).cpu().numpy()
+        rep[f"K5_critic_values_vs_eager_fp32_{operands}"] = {
+            "rows": int(c["obs"].shape[0]), "value_std": float(c["values"].std()),
+            "max_abs_err": float(np.abs(v - c["values"]).max()), "rms_err": float(np.sqrt(((v - c["values"]) ** 2).mean()))}
+    rep["K5_auto_operands"] = dd.PolicyBlob(sd, device=DEV).operand_dtype
+    # ... and at size: every observation row of a cfg-4 rollout (65,536 envs x 250 steps) through the eager fp32 torch networks
+    from torch_reference import reference_policy
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for operands in ("fp16", "bf16"):
+        blob, vb = dd.PolicyBlob(sd, device=DEV, operands=operands), dd.ValueBlob(sdc, device=DEV, operands=operands)
+        env = dd.BatchedDroneEnv(65536, device=DEV, seed=2, randomize_drone=True, randomize_platform=True, max_steps=250,
+                                 auto_reset=True, dtype=torch.float32)
+        env.reset()
+        out = dd.policy_rollout(env, blob, 250, sample=True, want="op")
+        rows, probs, vals = out["obs"].view(-1, 15), out["probs"].view(-1, 3), dd.value_forward(vb, out["obs"]).view(-1)
+        pol, crit = reference_policy(sd).to(DEV), reference_policy(sdc, head=1).to(DEV)
+        perr = verr = flip_logit = 0.0; psq = vsq = vsc = 0.0; nflip = 0
+        with torch.no_grad():
+            for lo in range(0, rows.shape[0], 1 << 20):
+                x = rows[lo:lo + (1 << 20)]
+                pr = pol(x); dp = (probs[lo:lo + (1 << 20)] - pr).abs()
+                perr = max(perr, dp.max().item()); psq += dp.double().pow(2).sum().item()
+                fl = (probs[lo:lo + (1 << 20)] > 0.5) != (pr > 0.5); nflip += int(fl.sum().item())
+                logit = torch.log(pr.clamp_min(1e-30)) - torch.log1p(-pr.clamp_max(1 - 1e-7))
+                flip_logit = max(flip_logit, (logit.abs() * fl).max().item())
+                vr = crit(x).squeeze(-1); dv = (vals[lo:lo + (1 << 20)] - vr).abs()
+                verr = max(verr, dv.max().item()); vsq += dv.double().pow(2).sum().item(); vsc += vr.double().pow(2).sum().item()
+        m = rows.shape[0]
+        rep[f"K5_cfg4_buffer_vs_eager_fp32_{operands}"] = {
+            "rows": m, "probs_max_abs_err": perr, "probs_rms_err": (psq / (3 * m)) ** 0.5, "threshold_flips": nflip,
+            "flip_rate_per_action": nflip / (3 * m), "max_|logit|_at_a_flip": flip_logit,
+            "critic_max_abs_err": verr, "critic_rms_err": (vsq / m) ** 0.5, "critic_value_rms": (vsc / m) ** 0.5}
+        del env, out, rows, probs, vals
+        torch.cuda.empty_cache()
     print(json.dumps(rep, indent=1))
 
 

@@ -132,6 +132,19 @@ def test_step_host_modes_are_identical():
             for k_, ref in (("obs", obs), ("reward", rew), ("flags", fl)):
                 assert torch.equal(ioa[k_], iob[k_]), (n, t, k_)
                 assert torch.equal(ioa[k_], ref.cpu()), (n, t, k_)
+        # wait=False: the call returns an event; the results are in the pinned buffers once it has been waited for
+        side = torch.cuda.Stream("cuda:0")
+        side.wait_stream(torch.cuda.current_stream())
+        for t in range(5):
+            act = torch.randint(0, 8, (n,), generator=g, dtype=torch.uint8).pin_memory()
+            with torch.cuda.stream(side):
+                ev = a.step_host(ioa, actions=act, wait=False)
+            b.step_host(iob, actions=act)
+            ev.synchronize()
+            for k_ in ("obs", "reward", "flags"):
+                assert torch.equal(ioa[k_], iob[k_]), (n, t, k_)
+            c.step_raw(act.to("cuda:0"))
+        torch.cuda.current_stream().wait_stream(side)
         sa, sb = a.get_state(), b.get_state()
         for k_ in sa:
             assert torch.equal(torch.nan_to_num(sa[k_].double(), nan=-1.0), torch.nan_to_num(sb[k_].double(), nan=-1.0)), k_
