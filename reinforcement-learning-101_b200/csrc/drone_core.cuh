@@ -221,6 +221,7 @@ DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward,
     vy = A::mul(vy, k.drag);
     const R x = A::add(e.x, vx);
     const R y = A::add(e.y, vy);
+    const R w_add = w;                                     // the angular velocity the angle advances by this step
     R ang = A::add(e.angle, w);
     w = A::mul(w, k.ang_drag);
     if (A::abs_(ang) > (R)180) {                           // physics.py:35-39 (rarely taken)
@@ -251,14 +252,38 @@ DD_HD uint32_t step_core(Env<R>& e, uint32_t act, const Consts<R>& k, R& reward,
     // test that and the two cheap conditions before paying for sin/cos of the post-update angle.
     if (!(speed2 > k.speed2_max) && A::abs_(ang) <= k.land_angle &&
         A::abs_(ddx) <= k.reach_x && A::abs_(ddy) <= k.reach_y) {
-        R s, c;
-        A::sincos_deg(ang, s, c);
-        const R bx = A::fma_(-k.half_h, s, x);             // x + (0*c - 10*s)  drone.py:136-137
-        const R by = A::fma_(k.half_h, c, y);              // y + (0*s + 10*c)
-        if ((e.px - k.plat_half_w <= bx) && (bx <= e.px + k.plat_half_w) &&
-            (e.py - k.plat_half_h <= by) && (by <= e.py + k.plat_half_h)) {      // platform.py:74
-            f = DD_DONE | DD_LANDED; r = k.rs_land;
+        bool decided = false, inside = false;
+        if constexpr (PRE_SC && sizeof(R) == 4) {
+            // The caller holds sin / cos of the PRE-update angle (computed off the critical path).  The post-update
+            // angle is that plus w_add (|w_add| is a few degrees), so sin / cos of it follow from the angle-addition
+            // formulas and two short polynomials -- no range reduction, no MUFU -- to ~2e-7.  That is only used to
+            // DECIDE: if the bottom-centre point so obtained is farther than 1e-3 px from every edge of the platform
+            // box (the exact evaluation below differs from it by < 1e-4 px), inside / outside is certain and equals the
+            // exact decision bit for bit; otherwise (probability ~1e-5 per test) the exact path runs.  The landing test
+            // sits on the serial chain of the fused policy kernel, where sincospif's latency is paid by the whole tile.
+            if (A::abs_(w_add) <= (R)8) {
+                const R th = w_add * (R)0.017453292519943295, t2 = th * th;
+                const R sn = th * ((R)1 + t2 * ((R)-0.16666666666666666 + t2 * (R)0.008333333333333333));
+                const R cs = (R)1 + t2 * ((R)-0.5 + t2 * ((R)0.041666666666666664 + t2 * (R)-0.001388888888888889));
+                const R sa = s_pre * cs + c_pre * sn, ca = c_pre * cs - s_pre * sn;
+                const R bxa = x - k.half_h * sa, bya = y + k.half_h * ca;
+                const R x0 = e.px - k.plat_half_w, x1 = e.px + k.plat_half_w, y0 = e.py - k.plat_half_h, y1 = e.py + k.plat_half_h;
+                const R mx = fminf(A::abs_(bxa - x0), A::abs_(bxa - x1)), my = fminf(A::abs_(bya - y0), A::abs_(bya - y1));
+                if (fminf(mx, my) > (R)1e-3) {
+                    decided = true;
+                    inside = (x0 <= bxa) && (bxa <= x1) && (y0 <= bya) && (bya <= y1);
+                }
+            }
         }
+        if (!decided) {
+            R s, c;
+            A::sincos_deg(ang, s, c);
+            const R bx = A::fma_(-k.half_h, s, x);         // x + (0*c - 10*s)  drone.py:136-137
+            const R by = A::fma_(k.half_h, c, y);          // y + (0*s + 10*c)
+            inside = (e.px - k.plat_half_w <= bx) && (bx <= e.px + k.plat_half_w) &&
+                     (e.py - k.plat_half_h <= by) && (by <= e.py + k.plat_half_h);      // platform.py:74
+        }
+        if (inside) { f = DD_DONE | DD_LANDED; r = k.rs_land; }
     }
     reward = r;
     e.ret = A::add(e.ret, r);                              // game_engine.py:131
@@ -442,6 +467,37 @@ DD_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
 
 // DroneGame.reset(), game_engine.py:59-93 + drone.py:221-238 + platform.py:104-114.
 // `episode` is the number of resets this env has had so far (the Philox counter).
+// The four spawn coordinates of episode `episode` of env `env_id` (the random part of reset()).
+template <typename R>
+DD_HD void spawn_draw(const Consts<R>& k, uint64_t seed, uint64_t env_id, uint32_t episode, bool rand_drone, bool rand_platform,
+                      R& x, R& y, R& px, R& py)
+{
+    Env<R> e;
+    e.x = k.start_x; e.y = k.start_y; e.px = k.plat_x; e.py = k.plat_y;
+    if (rand_drone || rand_platform) {
+        const U4 r = philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), episode, 0u,
+                                   (uint32_t)seed, (uint32_t)(seed >> 32));
+        if (rand_drone) {                                  // np.random.randint(lo, hi + 1)
+            e.x = k.spawn_x_min + (R)mulhi_u32(r.a, k.spawn_x_count);
+            e.y = k.spawn_y_min + (R)mulhi_u32(r.b, k.spawn_y_count);
+        }
+        if (rand_platform) {                               // np.random.randint(lo, hi)
+            e.px = k.plat_x_min + (R)mulhi_u32(r.c, k.plat_x_count);
+            e.py = k.plat_y_min + (R)mulhi_u32(r.d, k.plat_y_count);
+        }
+    }
+    x = e.x; y = e.y; px = e.px; py = e.py;
+}
+
+// reset() given the spawn coordinates: everything else of a fresh episode
+template <typename R>
+DD_HD void spawn_apply(Env<R>& e, const Consts<R>& k, R x, R y, R px, R py)
+{
+    e.x = x; e.y = y; e.px = px; e.py = py;
+    e.vx = (R)0; e.vy = (R)0; e.angle = (R)0; e.angvel = (R)0;
+    e.fuel = k.max_fuel; e.ret = (R)0; e.steps = 0;
+}
+
 template <typename R>
 DD_HD void spawn(Env<R>& e, const Consts<R>& k, uint64_t seed, uint64_t env_id, uint32_t episode,
                  bool rand_drone, bool rand_platform)

@@ -42,14 +42,29 @@
 //   * the last layer (64 -> 3) and the sigmoid / Bernoulli / log-prob are folded into the third
 //     epilogue on the CUDA cores; the environment step is `step_core` from drone_core.cuh, the
 //     same code as K1, so the environment side is bit-identical to dd_rollout on the same actions.
+//   * layer 3 takes its A operand from TENSOR memory (tcgen05.mma "TS" form): the second epilogue writes the packed
+//     16-bit activations with tcgen05.st into columns [0, 64) of its own accumulator -- columns pass 2 has already
+//     consumed -- and D3 accumulates in columns [64, 128).  That takes the 32 KB A2 store and the 32 KB A2 operand read
+//     of every tile-step off shared memory (an SS-form K-block streams 4 KB of A + 4 KB of B through the 128 B/clk
+//     port, as fast as the tensor pipe consumes them): -12..18 % on the forward-only kernels, -0.5 % on the rollout.
+//     Layers 1 -> 2 cannot do the same: A1 (64 columns) + D2 (128) do not fit a tile's 128 columns;
+//   * off the serial chain, in registers: the spawn of the env's NEXT episode is drawn ahead of time (a reset on the
+//     chain is a few moves; the 10 Philox rounds of the spawn after it run under the second MMA of the following
+//     step), and the landing test -- which a trained policy enters on most tile-steps -- decides from the angle-addition
+//     formulas on the pre-update sin / cos already held, falling back to sincospif only within 1e-3 px of a platform
+//     edge (step_core<.., PRE_SC>: same decisions bit for bit): 1.250 -> 1.220 ms.
 // The four tiles of a CTA are independent pipelines, so while one waits for its MMAs the other three
 // keep the CUDA cores busy; work that is not on the chain obs -> network -> action -> env step -> obs runs in
 // the shadow of an MMA, where the warp would otherwise sleep: the previous step's log-prob / output stores /
 // statistics under the first, the Philox draws under the second, sin / cos of the pre-update angle under the
-// third.  Measured:
-// T(k tiles per SM) = 0.70 ms + k x 0.21 ms per 250 steps -- the slope is the issue slots of one more warp
-// per scheduler (~1,700 instructions per env-step), the intercept the latency of one tile's serial chain;
-// the tensor pipe is ~40 % busy.
+// third.  Measured on B200, cfg 4 (profiles/r02_k5_ablation.json): 1.22 ms per 65,536 x 250 launch,
+// 1,445 instructions per env-step, issue slots 64 % busy, tensor pipe 47 %.  T(k tiles per SM) = 0.72 / 0.86 / 1.02 /
+// 1.26 ms: one tile alone needs 5,500 cycles per step (its chain: 3 x {fence, barrier, MMA, mbarrier, TMEM read,
+// two-pass LayerNorm}, sample, env step), four tiles overlap to 9,300.  Removing one part at a time (timing only)
+// takes off: LayerNorm pass 2 + conversions + A stores + last Linear 0.49 ms, the MMAs 0.26, the env step 0.20,
+// output stores 0.08, LayerNorm pass 1 0.02, the sampling Philox 0.00 -- the parts add up to the whole: a serial
+// chain per tile.  Tried and rejected this round: deferred outputs under the second MMA (+1 %), all four warps
+// waiting on the MMA mbarrier / suspend-time hints (+0.3..1.3 %), phase-shifted tile starts (0 %).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -92,9 +107,12 @@ constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this
 #ifndef DD_K5_CHUNK
 #define DD_K5_CHUNK 16
 #endif
-#ifndef DD_K5_FLUSH_AT
-#define DD_K5_FLUSH_AT 1                       // under which MMA of the next step the deferred outputs of a step are written
+#ifndef DD_K5_TS_LAYER3
+#define DD_K5_TS_LAYER3 1                      // layer 3 reads its A operand from TMEM (tcgen05.mma "TS" form), see the header comment
 #endif
+#ifndef DD_K5_ABLATE
+#define DD_K5_ABLATE 0                         // profiling only (wrong results): 1 no MMA issue, 2 no env step, 4 no Philox,
+#endif                                         //   8 no output stores / obs staging, 16 no LayerNorm pass 1, 32 no pass 2
 constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (8, 16 or 32; 16 measured best)
 
 constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
@@ -135,25 +153,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-#ifndef DD_K5_WAIT_HINT_NS
-#define DD_K5_WAIT_HINT_NS 0                   // > 0: suspend-time hint of mbarrier.try_wait (the warp sleeps in hardware)
-#endif
-#ifndef DD_K5_ALL_WARPS_WAIT
-#define DD_K5_ALL_WARPS_WAIT 0                 // 1: all four warps of a tile wait on the MMA mbarrier (no second named barrier)
-#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-#if DD_K5_WAIT_HINT_NS > 0
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)DD_K5_WAIT_HINT_NS) : "memory");
-#else
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-#endif
     return ok != 0;
 }
 // A lost MMA / TMA completion must fault, never hang the GPU -- but the bound is WALL TIME (%globaltimer, 20 s),
@@ -181,19 +186,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "n"(kTile) : "memory"); }
-// Wait for the tile's committed MMAs.  Only the issuing warp polls the mbarrier (try_wait returns after a short
+// Wait for the tile's committed MMAs.  (Round 2 measured the alternatives on B200 -- all four warps waiting on the
+// mbarrier, with and without a suspend-time hint: 1.265 / 1.278 ms against 1.262 for this scheme.)  Only the issuing warp polls the mbarrier (try_wait returns after a short
 // system-defined time, so a waiting warp keeps executing a poll loop that competes for issue slots: ~200
 // instructions per thread-step when all four warps of a tile poll); the other three block on a second named
 // barrier that the issuing warp joins once the phase has flipped.
 __device__ __forceinline__ void wait_mma(uint32_t bar, uint32_t& phase, bool issuer_warp, int g) {
-#if DD_K5_ALL_WARPS_WAIT
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-#else
     if (issuer_warp) mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("bar.sync %0, %1;" :: "r"(g + 1 + kGroups), "n"(kTile) : "memory");
-#endif
     tc_fence_after();
 }
 
@@ -210,11 +211,28 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool f16) {
     return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (DD_K5_ABLATE & 1) return;
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory ("TS" form): row r of the 128 x 16 A block is TMEM lane r, its 16 sixteen-bit elements are
+// the 8 thirty-two-bit columns starting at `tmem_a` (element 2j in the low half of column j).
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (DD_K5_ABLATE & 1) return;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 thirty-two-bit columns of this thread's TMEM lane <- 8 registers (16 packed sixteen-bit activations)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&w)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
@@ -317,6 +335,7 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&beta)[N
 #pragma unroll
     for (int j = 0; j < 4; ++j) q[j] = make_float2(0.f, 0.f);
     buf[0].issue(trow);
+    if (!(DD_K5_ABLATE & 16)) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         buf[c & 1].wait();
@@ -327,9 +346,11 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&beta)[N
             q[j & 3] = __ffma2_rn(t, t, q[j & 3]);
         }
     }
+    }
     const float sq = ((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y));
     const float rstd = rsqrtf(fmaf(sq, 1.0f / N, 1e-5f));                  // biased variance, like nn.LayerNorm
     const float2 r2 = make_float2(rstd, rstd);
+    if (DD_K5_ABLATE & 32) { buf[0].wait(); return; }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         buf[c & 1].wait();
@@ -355,6 +376,20 @@ __device__ __forceinline__ void store_a_chunk_relu(uint8_t* a_tile, int row, int
         w.x = pack16_relu<F16>(y[8 * q + 0], y[8 * q + 1]); w.y = pack16_relu<F16>(y[8 * q + 2], y[8 * q + 3]);
         w.z = pack16_relu<F16>(y[8 * q + 4], y[8 * q + 5]); w.w = pack16_relu<F16>(y[8 * q + 6], y[8 * q + 7]);
         *reinterpret_cast<uint4*>(a_tile + ((CH / 8) * c + q) * (kTile * 16) + row * 16) = w;
+    }
+}
+
+// ReLU + write CH activations of my row as fp16 / bf16 into the TMEM A operand of the next layer: K columns CH*c .. CH*c+CH-1
+// are the CH/2 thirty-two-bit columns starting at ta + (CH/2)*c.
+template <int CH, bool F16>
+__device__ __forceinline__ void store_a_chunk_relu_tmem(uint32_t ta, int c, const float (&y)[CH]) {
+    static_assert(CH % 16 == 0, "one tcgen05.st.x8 per 16 activations");
+#pragma unroll
+    for (int q = 0; q < CH / 16; ++q) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack16_relu<F16>(y[16 * q + 2 * j], y[16 * q + 2 * j + 1]);
+        tmem_st8(ta + (uint32_t)((CH / 2) * c + 8 * q), w);
     }
 }
 
@@ -453,6 +488,17 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint64_t gid = a.env_id_base + (uint64_t)i;
     float speed = 0.f, dist = 0.f;
     if (!forward_only) speed_dist(e, speed, dist);
+    // The spawn of my env's NEXT episode (Philox(seed, env id, episode counter)) is drawn ahead of time and kept in
+    // registers: a reset on the serial chain is then a handful of moves, and the 10 Philox rounds of the spawn after
+    // it run under the second MMA of the following step (same spawn_draw as spawn(): bit-identical resets).
+    float nsx = 0.f, nsy = 0.f, nspx = 0.f, nspy = 0.f, nsdist = 0.f;
+    bool need_spawn = false;
+    auto draw_next_spawn = [&]() {
+        spawn_draw(k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0, nsx, nsy, nspx, nspy);
+        const float ddx = nspx - nsx, ddy = nspy - nsy;                       // speed_dist() of the fresh state
+        nsdist = Arith<float>::sqrt_(Arith<float>::fma_(ddx, ddx, Arith<float>::mul(ddy, ddy)));
+    };
+    if (!forward_only && live) draw_next_spawn();
     const bool shaping = !FAST && pa.shaped_tn != nullptr;
     // The tile's observations of one step are 128 x 15 contiguous floats of obs_tn: full, 16-byte aligned tiles
     // are staged in shared memory (stride 15 words: conflict-free) and leave with one cp.async.bulk per step.
@@ -474,6 +520,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     // step, where the warp would otherwise sleep, instead of in front of it on the tile's serial chain.
     struct Pending { float p0, p1, p2, reward, shaped, ret_stat; uint32_t act, oflags, f_stat; int32_t len_stat; } pend = {};
     auto flush_pending = [&](size_t o_prev) {
+        if (DD_K5_ABLATE & 8) return;
         if (live) {
             if (shaping) pa.shaped_tn[o_prev] = pend.shaped;
             if (out_act) pa.actions_tn[o_prev] = (uint8_t)pend.act;
@@ -537,7 +584,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         }
         // under the first MMA: the observation leaves (staged for the TMA store issued after the next barrier, or
         // directly for ragged / unaligned tiles), and the previous step's deferred outputs
-        if (obs_bulk) {
+        if (obs_bulk && !(DD_K5_ABLATE & 8)) {
 #pragma unroll
             for (int j = 0; j < kIn; ++j) s_obs[row * kIn + j] = ob[j];
         }
@@ -546,9 +593,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
         }
-#if DD_K5_FLUSH_AT == 1
-        if (!forward_only && t > 0) flush_pending(o - a.n);
-#endif
+        if (!forward_only && t > 0) flush_pending(o - a.n);   // (under the second MMA instead: measured slower, 1.270 vs 1.257 ms)
         wait_mma(bar, phase, issuer_warp, g);
         ln_epilogue<kH1, CH>(trow, pc.beta0,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH, F16>(s_a, row, c, y); });
@@ -568,16 +613,37 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w1b_addr, kH2 * 16, 128), umma_idesc(128, kH2, F16), 1u);
             umma_commit(bar);
         }
-#if DD_K5_FLUSH_AT == 2
-        if (!forward_only && t > 0) flush_pending(o - a.n);  // under the second (longest) MMA: the previous step's deferred outputs
-#endif
         U4 rnd = {0u, 0u, 0u, 0u};                           // under the second MMA: this step's Philox draws
-        if (!forward_only && !thresholded) {
+        if (!forward_only && need_spawn) { draw_next_spawn(); need_spawn = false; }   // refill after a reset (off the chain)
+        if (!forward_only && !thresholded && !(DD_K5_ABLATE & 4)) {
             rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), pa.t0 + (uint32_t)t, 2u,
                                 (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             pin(rnd.a); pin(rnd.b); pin(rnd.c);
         }
         wait_mma(bar, phase, issuer_warp, g);
+#if DD_K5_TS_LAYER3
+        // The activations of layer 2 go to TENSOR memory, not shared memory: A2 (128 lanes x 64 columns of packed 16-bit
+        // pairs) overlays the columns [0, 64) of D2 that pass 2 has already consumed (chunk c reads D2 columns
+        // [16c, 16c+16) and writes A2 columns [8c, 8c+8)), layer 3 reads its A operand from there (TS form) and
+        // accumulates D3 in columns [64, 128).  Shared memory is what bounds this kernel (each SS-form K-block streams
+        // 4 KB of A + 4 KB of B through the 128 B/clk port, on top of the epilogues' stores): this takes the 32 KB A2
+        // store and the 32 KB A2 operand read of every tile-step off it.
+        ln_epilogue<kH2, CH>(trow, pc.beta1,
+                             [&](int c, const float (&y)[CH]) { store_a_chunk_relu_tmem<CH, F16>(trow, c, y); });
+        tmem_st_wait();
+        // ---------------- layer 3: D[128x64] = A2[128x128] (TMEM) * W2''^T + ones * bias2''^T --------------
+        if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
+        tc_fence_before(); group_bar(g);
+        if (issuer_warp && elect_one()) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kH2 / 16; ++j)
+                umma_ts(tmem_d + 64u, tmem_d + (uint32_t)(8 * j),
+                        umma_desc(w2_addr + j * 2 * (kH3 * 16), kH3 * 16, 128), umma_idesc(128, kH3, F16), j > 0 ? 1u : 0u);
+            umma_bf16(tmem_d + 64u, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3, F16), 1u);
+            umma_commit(bar);
+        }
+#else
         ln_epilogue<kH2, CH>(trow, pc.beta1,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH, F16>(s_a, row, c, y); });
         // ---------------- layer 3: D[128x64] = A2[128x128] * W2''^T + ones * bias2''^T ------------------
@@ -592,12 +658,13 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_bf16(tmem_d, umma_desc(ones_addr, kTile * 16, 128), umma_desc(w2b_addr, kH3 * 16, 128), umma_idesc(128, kH3, F16), 1u);
             umma_commit(bar);
         }
+#endif
         float s_pre = 0.f, c_pre = 1.f;                      // under the third MMA: sin / cos of the pre-update angle
         if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }   // (main thrust, drone.py:58-66)
         wait_mma(bar, phase, issuer_warp, g);
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
-        ln_epilogue<kH3, CH>(trow, pc.beta2, [&](int c, const float (&y)[CH]) {
+        ln_epilogue<kH3, CH>(trow + (DD_K5_TS_LAYER3 ? 64u : 0u), pc.beta2, [&](int c, const float (&y)[CH]) {
 #pragma unroll
             for (int j = 0; j < CH / 4; ++j) {
                 const float2 h0 = make_float2(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f));      // ReLU
@@ -647,7 +714,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         uint32_t oflags = pflags, f_stat = 0;
         float ret_stat = 0; int32_t len_stat = 0;
         float reward = 0.f, shaped = 0.f;
-        if (live && !(pflags & DD_DONE)) {
+        if (live && !(pflags & DD_DONE) && !(DD_K5_ABLATE & 2)) {
             uint32_t f = step_core<float, true, true>(e, act, k, reward, speed, dist, s_pre, c_pre);
             if (!f && max_steps > 0 && e.steps >= max_steps) f = DD_DONE | DD_TRUNCATED;
             oflags = f;
@@ -659,11 +726,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             if (f) {
                 f_stat = f; ret_stat = e.ret; len_stat = e.steps;
                 if (auto_reset) {
-                    spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
+                    spawn_apply(e, k, nsx, nsy, nspx, nspy);                   // == spawn(e, ..., ep): drawn ahead of time
                     ep += 1;
+                    need_spawn = true;
                     platform_dirty = true;
                     f = 0;
-                    speed_dist(e, speed, dist);
+                    speed = 0.f; dist = nsdist;                               // == speed_dist(e, ...) of a fresh episode (v = 0)
                     if (shaping) { dprev = nan_of<float>(); dcur = Arith<float>::div(dist, k.width, k.inv_width); }
                 }
             }
