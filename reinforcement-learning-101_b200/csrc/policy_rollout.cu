@@ -112,7 +112,7 @@ constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this
 #endif
 #ifndef DD_K5_ABLATE
 #define DD_K5_ABLATE 0                         // profiling only (wrong results): 1 no MMA issue, 2 no env step, 4 no Philox,
-#endif                                         //   8 no output stores / obs staging, 16 no LayerNorm pass 1, 32 no pass 2
+#endif                                         //   8 no output stores / obs staging, 16 no LayerNorm pass 1, 32 no pass 2, 64 / 128 one beta / w3 constant for all columns
 constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (8, 16 or 32; 16 measured best)
 
 constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
@@ -358,7 +358,7 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&beta)[N
         float y[CH];
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
-            const int col = c * CH + 4 * j;              // compile-time after unrolling: c[0][imm] -> uniform registers
+            const int col = (DD_K5_ABLATE & 64) ? 0 : c * CH + 4 * j;   // compile-time after unrolling: c[0][imm] -> uniform registers
             const float2 y0 = __ffma2_rn(f2_of(buf[c & 1], 2 * j), r2, make_float2(beta[col], beta[col + 1]));
             const float2 y1 = __ffma2_rn(f2_of(buf[c & 1], 2 * j + 1), r2, make_float2(beta[col + 2], beta[col + 3]));
             y[4 * j] = y0.x; y[4 * j + 1] = y0.y; y[4 * j + 2] = y1.x; y[4 * j + 3] = y1.y;
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < CH / 4; ++j) {
                 const float2 h0 = make_float2(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f));      // ReLU
                 const float2 h1 = make_float2(fmaxf(y[4 * j + 2], 0.f), fmaxf(y[4 * j + 3], 0.f));
-                const int col = c * CH + 4 * j;
+                const int col = (DD_K5_ABLATE & 128) ? 0 : c * CH + 4 * j;
                 za = __ffma2_rn(h0, make_float2(pc.w3[0][col], pc.w3[0][col + 1]), za); za = __ffma2_rn(h1, make_float2(pc.w3[0][col + 2], pc.w3[0][col + 3]), za);
                 if (HEAD == 3) {
                     zb = __ffma2_rn(h0, make_float2(pc.w3[1][col], pc.w3[1][col + 1]), zb); zb = __ffma2_rn(h1, make_float2(pc.w3[1][col + 2], pc.w3[1][col + 3]), zb);

@@ -36,6 +36,22 @@ from . import _native as nv
 from .env import BatchedDroneEnv
 
 
+def schedule_pieces(t: int, k: int, num_shards: int, trace_len: int):
+    """The trace schedule as plain integers: launches t .. t+k-1 of an env's life, cut into pieces of at most one
+    period (S * L launches).  Yields ``(offset_in_period, length, [(shard, trace_row), ...])`` per piece; launch j
+    steps shard ``j % S`` with trace row ``(j // S) % L``.  (offset, length) identifies a piece: its job list
+    depends on nothing else, which is what makes the graph cache of ``ShardedDroneEnv.run`` exact."""
+    S, L = int(num_shards), int(trace_len)
+    period = S * L
+    t, k = int(t), int(k)
+    while k > 0:
+        off = t % period
+        seg = min(k, period)
+        yield off, seg, [((off + j) % S, ((off + j) // S) % L) for j in range(seg)]
+        t += seg
+        k -= seg
+
+
 class ShardedDroneEnv:
     def __init__(self, num_shards: int, envs_per_shard: int, device="cuda", chains: int = 2, trace_len: int = 16,
                  use_graphs: bool = True, max_graphs: int = 256, env_id_base: int = 0, launch_flags: int = nv.LAUNCH_PDL,
@@ -168,17 +184,9 @@ class ShardedDroneEnv:
         """Advance the trace schedule by ``k`` launches (see the module docstring)."""
         if self.trace is None:
             raise RuntimeError("call set_trace() / random_trace() before run()")
-        k = int(k)
-        period = self.S * self.L
-        while k > 0:
-            off = self.t % period
-            seg = min(k, period)                            # a piece may wrap around the period: rows are taken mod L
-            self._play(("run", off, seg, want_obs),
-                       lambda: [((off + j) % self.S, self.trace[((off + j) // self.S) % self.L, (off + j) % self.S])
-                                for j in range(seg)],
-                       want_obs)
+        for off, seg, jobs in schedule_pieces(self.t, k, self.S, self.L):   # a piece may wrap around the period
+            self._play(("run", off, seg, want_obs), lambda: [(s, self.trace[row, s]) for s, row in jobs], want_obs)
             self.t += seg
-            k -= seg
 
     def step_all(self, actions: Optional[torch.Tensor] = None, want_obs: bool = True):
         """One step of EVERY shard.  ``actions``: uint8 [S, N] packed actions, copied into the static buffer

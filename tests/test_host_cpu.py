@@ -182,3 +182,46 @@ def test_step_schedule_is_the_notebook_formula():
     assert np.array_equal(s, np.round(300 + 200 * x ** 0.65).astype(np.int32))
     assert s[0] == 300 and s[-1] == 500 and s.dtype == np.int32 and np.all(np.diff(s) >= 0)
     assert dd.step_schedule(8, 75, 250).tolist() == [75, 124, 153, 176, 197, 216, 233, 250]
+
+
+def test_sharded_schedule_is_a_pure_function_of_offset_and_length():
+    """ShardedDroneEnv.run: launch j steps shard j % S with trace row (j // S) % L; a piece is identified by
+    (offset in the S*L period, length) -- the same key must always mean the same job list (graph cache), whatever
+    sequence of run(k) calls led there, and consecutive pieces must tile the launch sequence without gaps."""
+    sharded = importlib.import_module("reinforcement-learning-101_b200.sharded")
+    for S, L in ((6, 16), (3, 4), (1, 5), (4, 1)):
+        period = S * L
+        seen = {}
+        t = 0
+        for k in (1, 5, 20, 20, 20, 7, 12, 1, 30, 2 * period + 3, 20, period, 19):
+            flat = []
+            for off, seg, jobs in sharded.schedule_pieces(t, k, S, L):
+                assert 0 <= off < period and 1 <= seg <= period and len(jobs) == seg and off == (t + len(flat)) % period
+                assert seen.setdefault((off, seg), jobs) == jobs                 # same key -> same jobs, always
+                flat += jobs
+            assert flat == [(j % S, (j // S) % L) for j in range(t, t + k)]      # exactly launches t .. t+k-1, in order
+            t += k
+        # every shard sees its trace rows in order, one row per visit
+        visits = {}
+        for j in range(t):
+            s, row = j % S, (j // S) % L
+            assert row == visits.get(s, 0) % L
+            visits[s] = visits.get(s, 0) + 1
+    assert list(sharded.schedule_pieces(5, 0, 6, 16)) == []
+
+
+def test_packed_output_layout():
+    """The per-step output block [obs | reward | flags] that step_host moves with one copy: 256-byte aligned parts,
+    no overlap, sized for both dtypes and both observation strides."""
+    envmod = importlib.import_module("reinforcement-learning-101_b200.env")
+    for n in (0, 1, 255, 4096, 1 << 20):
+        for stride in (15, 16):
+            for dt, isz in ((torch.float32, 4), (torch.float64, 8)):
+                o_obs, o_rew, o_flg, end = envmod._out_layout(n, stride, dt)
+                assert o_obs == 0 and o_rew % 256 == 0 and o_flg % 256 == 0 and end % 256 == 0
+                assert o_rew >= n * stride * isz and o_flg >= o_rew + n * isz and end >= o_flg + n and end >= 256
+                blk = torch.zeros(end, dtype=torch.uint8)
+                obs, rew, fl = envmod._carve(blk, (o_obs, o_rew, o_flg, end), n, stride, dt)
+                assert obs.shape == (n, stride) and rew.shape == (n,) and fl.shape == (n,) and obs.dtype == dt
+                obs.fill_(1); rew.fill_(2); fl.fill_(3)
+                assert int(blk[o_rew:o_rew + n * isz].view(dt).sum().item()) == 2 * n and int(fl.sum().item()) == 3 * n
