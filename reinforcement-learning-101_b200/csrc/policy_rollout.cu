@@ -110,6 +110,9 @@ constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this
 #ifndef DD_K5_TS_LAYER3
 #define DD_K5_TS_LAYER3 1                      // layer 3 reads its A operand from TMEM (tcgen05.mma "TS" form), see the header comment
 #endif
+#ifndef DD_K5_TRACE
+#define DD_K5_TRACE 0                          // profiling only: CTA 0 records globaltimer-free clock64 stamps per tile / step / phase
+#endif
 #ifndef DD_K5_ABLATE
 #define DD_K5_ABLATE 0                         // profiling only (wrong results): 1 no MMA issue, 2 no env step, 4 no Philox,
 #endif                                         //   8 no output stores / obs staging, 16 no LayerNorm pass 1, 32 no pass 2, 64 / 128 one beta / w3 constant for all columns
@@ -126,6 +129,14 @@ constexpr int kSmemObs = kSmemBar + 80;                             //   contigu
                                                                     //   (bar area: 4 MMA + 4 obs-load mbarriers, TMEM base)
 constexpr int kSmemTotal = kSmemObs + kGroups * kObsTileBytes;      // 225,344 of the 232,448 B
 static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
+
+#if DD_K5_TRACE
+constexpr int kTraceSteps = 24, kTracePts = 12;
+__device__ long long g_k5_trace[4][kTraceSteps][kTracePts];
+#define DD_TRACE(pt) do { if (blockIdx.x == 0 && (threadIdx.x & 127) == 0 && t >= 100 && t < 100 + kTraceSteps) g_k5_trace[g][t - 100][pt] = clock64(); } while (0)
+#else
+#define DD_TRACE(pt) do { } while (0)
+#endif
 
 struct PArgs {
     DDPolicyConsts pc;     // per-column LN parameters + last layer: constant bank -> uniform operands
@@ -540,6 +551,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     for (int32_t t = 0; t < pa.T; ++t) {
         const size_t o = FWD ? (size_t)i : (size_t)t * a.n + i;
         // ---------------- observation -> A0 (bf16, K = 16: 15 inputs + constant 1 for the bias) -------
+        DD_TRACE(0);                                         // step start
         float ob[16];
         const bool tile_in = FWD && tile_bulk_in(tile0);     // warp-uniform: this tile's rows are in s_obs (or on their way)
         if (forward_only) {
@@ -570,7 +582,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             *reinterpret_cast<uint4*>(s_a + (2 + q) * (kTile * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         // ---------------- layer 1: D[128x128] = A0[128x16] * W0''^T, split bf16 (3 MMAs) ---------------
+        DD_TRACE(1);                                         // A0 written
         fence_async_smem(); tc_fence_before(); group_bar(g);
+        DD_TRACE(2);                                         // past barrier 1
         if (issuer_warp && elect_one()) {
             tc_fence_after();
             umma_bf16(tmem_d, umma_desc(a_addr, kTile * 16, 128), umma_desc(w0_addr, kH1 * 16, 128), umma_idesc(128, kH1, F16), 0u);      // x_hi W_hi
@@ -594,10 +608,13 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
         }
         if (!forward_only && t > 0) flush_pending(o - a.n);   // (under the second MMA instead: measured slower, 1.270 vs 1.257 ms)
+        DD_TRACE(3);                                         // shadow work 1 done
         wait_mma(bar, phase, issuer_warp, g);
+        DD_TRACE(4);                                         // MMA1 done
         ln_epilogue<kH1, CH>(trow, pc.beta0,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu<CH, F16>(s_a, row, c, y); });
         // ---------------- layer 2: D[128x128] = A1[128x128] * W1''^T + ones * bias1''^T -----------------
+        DD_TRACE(5);                                         // epilogue 1 done
         fence_async_smem(); tc_fence_before(); group_bar(g);
         if (issuer_warp && elect_one()) {
             tc_fence_after();
@@ -620,7 +637,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                                 (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             pin(rnd.a); pin(rnd.b); pin(rnd.c);
         }
+        DD_TRACE(6);                                         // shadow work 2 done
         wait_mma(bar, phase, issuer_warp, g);
+        DD_TRACE(7);                                         // MMA2 done
 #if DD_K5_TS_LAYER3
         // The activations of layer 2 go to TENSOR memory, not shared memory: A2 (128 lanes x 64 columns of packed 16-bit
         // pairs) overlays the columns [0, 64) of D2 that pass 2 has already consumed (chunk c reads D2 columns
@@ -631,6 +650,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         ln_epilogue<kH2, CH>(trow, pc.beta1,
                              [&](int c, const float (&y)[CH]) { store_a_chunk_relu_tmem<CH, F16>(trow, c, y); });
         tmem_st_wait();
+        DD_TRACE(8);                                         // epilogue 2 done
         // ---------------- layer 3: D[128x64] = A2[128x128] (TMEM) * W2''^T + ones * bias2''^T --------------
         if (obs_bulk && issuer_warp && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile reusable after this barrier
         tc_fence_before(); group_bar(g);
@@ -661,7 +681,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #endif
         float s_pre = 0.f, c_pre = 1.f;                      // under the third MMA: sin / cos of the pre-update angle
         if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }   // (main thrust, drone.py:58-66)
+        DD_TRACE(9);                                         // shadow work 3 done
         wait_mma(bar, phase, issuer_warp, g);
+        DD_TRACE(10);                                        // MMA3 done
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
         ln_epilogue<kH3, CH>(trow + (DD_K5_TS_LAYER3 ? 64u : 0u), pc.beta2, [&](int c, const float (&y)[CH]) {
@@ -678,6 +700,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             }
         });
         const float z0 = za.x + za.y + pc.b3[0], z1 = zb.x + zb.y + pc.b3[1], z2 = zc.x + zc.y + pc.b3[2];
+        DD_TRACE(11);                                        // epilogue 3 + last Linear done
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         // sigmoid with the approximate reciprocal (MUFU.RCP, ~1 ulp): the IEEE division sequence costs ~8 issue slots
         // per output on the chain; the same expression serves the rollout and the forward-only instantiation
@@ -951,6 +974,10 @@ static int forward_common(const void* blob, const DDPolicyConsts* consts, const 
 }  // namespace dd
 
 extern "C" {
+
+#if DD_K5_TRACE
+int dd_k5_trace_read(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, dd::g_k5_trace, sizeof(dd::g_k5_trace)); }
+#endif
 
 int dd_policy_pack(const DDPolicy* p, void* blob, DDPolicyConsts* consts, void* stream)
 {
