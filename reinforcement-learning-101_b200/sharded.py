@@ -75,7 +75,7 @@ class ShardedDroneEnv:
         self.trace: Optional[torch.Tensor] = None               # uint8 [L, S, N]
         self.actions = torch.zeros(self.S, self.N, dtype=torch.uint8, device=self.device)   # static input of step_all
         self._chains = [torch.cuda.Stream(self.device) for _ in range(self.C)]
-        self._graphs: "OrderedDict[tuple, torch.cuda.CUDAGraph]" = OrderedDict()
+        self._graphs: "OrderedDict[tuple, list]" = OrderedDict()   # piece key -> one CUDAGraph (or None) per chain
         self.graph_replays = 0
         self.eager_launches = 0
         self._dirty = False                                     # chain streams hold work the caller's stream has not joined
@@ -148,7 +148,7 @@ class ShardedDroneEnv:
             gs = self._capture(make_jobs(), want_obs)
             self._graphs[key] = gs
             while len(self._graphs) > self.max_graphs:
-                self._graphs.popitem(last=False)
+                self._retire(self._graphs.popitem(last=False)[1])
         else:
             self._graphs.move_to_end(key)
         for c, g in enumerate(gs):
@@ -175,8 +175,18 @@ class ShardedDroneEnv:
             gs.append(g)
         return gs
 
-    def _drop_graphs(self, kind: str) -> None:
-        for k in [k for k in self._graphs if k[0] == kind]:
+    def _retire(self, graphs) -> None:
+        """A captured graph may still be executing: wait for the chains before its executable is destroyed (rare path)."""
+        for ch in self._chains:
+            ch.synchronize()
+        del graphs
+
+    def _drop_graphs(self, kind: Optional[str] = None) -> None:
+        keys = [k for k in self._graphs if kind is None or k[0] == kind]
+        if keys:
+            for ch in self._chains:
+                ch.synchronize()
+        for k in keys:
             del self._graphs[k]
 
     # ---- stepping ---------------------------------------------------------------------------------------------
@@ -210,7 +220,7 @@ class ShardedDroneEnv:
         self.join()
         for e in self.shards:
             e.max_steps = v
-        self._graphs.clear()
+        self._drop_graphs()
 
     # ---- statistics / state -------------------------------------------------------------------------------------
     def stats_tensor(self) -> torch.Tensor:
