@@ -486,26 +486,35 @@ def run_ours(args):
         mom = torch.zeros(3, dtype=torch.float64, device=dev)
         mom1 = dd.advantage_moments(adv)
 
+        # the timing loops call the C ABI directly with pre-extracted pointers (3-4 us of host time per launch), so that
+        # the 15-40 us kernels are timed, not the Python wrappers' argument checks; every region is >= 30 ms.  Order =
+        # pipeline order: the GAE scan is timed right after the tensor-heavy critic forward, i.e. at the SM clock the
+        # power cap leaves then (stand-alone, at boost clock, the same launch takes 38 us instead of 42: profiles/README.md)
+        lib = dd.native.lib()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        p_rew, p_val, p_don, p_adv, p_mom = (pbuf["reward"].data_ptr(), vals.data_ptr(), dones.data_ptr(), adv.data_ptr(), mom_f.data_ptr())
+        p_rot = [t_.data_ptr() for t_ in rot]
+        p_out = [t_.data_ptr() for t_ in nrm_out]
+        p_mom1, p_momacc = mom1.data_ptr(), mom.data_ptr()
+
         def t_values(kk):
             for _ in range(kk):
                 dd.value_forward(vblob, pbuf["obs"], out=vals[:TP])
         def t_gae(kk):
             for _ in range(kk):
-                dd.gae(pbuf["reward"], vals, dones, out=adv, moments=mom_f)
+                lib.dd_gae_moments(p_rew, p_val, p_don, p_adv, None, p_mom, 0.99, 0.95, TP, NP, st)
         def t_mom(kk):
             for j in range(kk):
-                dd.advantage_moments(rot[j % 4], out=mom)
+                lib.dd_moments(p_rot[j % 4], ne, p_momacc, st)
         def t_nrm(kk):
-            lib = dd.native.lib()
-            st = torch.cuda.current_stream(dev).cuda_stream
             for j in range(kk):
-                lib.dd_normalize(rot[j % 2].data_ptr(), nrm_out[j % 2].data_ptr(), mom1.data_ptr(), 1e-8, ne, st)
-        rp = 4 * reps_p
+                lib.dd_normalize(p_rot[j % 2], p_out[j % 2], p_mom1, 1e-8, ne, st)
+        n_g, n_m, n_n = 800, 2000, 1200
         ms_v = timed(lambda: t_values(1), lambda: t_values(reps_p)) / reps_p
-        ms_g = timed(lambda: t_gae(2), lambda: t_gae(rp)) / rp
-        ms_m = timed(lambda: t_mom(4), lambda: t_mom(rp)) / rp
-        ms_n = timed(lambda: t_nrm(2), lambda: t_nrm(rp)) / rp
-        launches += reps_p + 3 * rp + 9
+        ms_g = timed(lambda: t_gae(4), lambda: t_gae(n_g)) / n_g
+        ms_m = timed(lambda: t_mom(8), lambda: t_mom(n_m)) / n_m
+        ms_n = timed(lambda: t_nrm(4), lambda: t_nrm(n_n)) / n_n
+        launches += reps_p + n_g + n_m + n_n + 17
         vtf = ne * FLOP_ROW_CRITIC / (ms_v * 1e-3) / 1e12
         others["critic_value_forward"] = {"bound": "tensor", "achieved": vtf, "peak": PK["bf16_sustained"], "unit": "TFLOP/s",
                                           "frac": vtf / PK["bf16_sustained"], "ms_per_launch": ms_v, "rows": ne}

@@ -14,13 +14,24 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 dd = importlib.import_module("reinforcement-learning-101_b200")
-ap = argparse.ArgumentParser(); ap.add_argument("--label", default=os.environ.get("DRONE_B200_LIB", "default")); ap.add_argument("--reps", type=int, default=200); ap.add_argument("--envs", type=int, default=65536)
+ap = argparse.ArgumentParser(); ap.add_argument("--label", default=os.environ.get("DRONE_B200_LIB", "default")); ap.add_argument("--reps", type=int, default=200); ap.add_argument("--envs", type=int, default=65536); ap.add_argument("--real", action="store_true", help="time the scan on the buffers of a real fused rollout (policy + critic checkpoints) instead of random data")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 n, T = a.envs, 250
 g = torch.Generator(device=dev).manual_seed(0)
 rew = torch.randn(T, n, device=dev, generator=g); val = torch.randn(T + 1, n, device=dev, generator=g)
 don = (torch.rand(T, n, device=dev, generator=g) < 0.01).to(torch.uint8)
+if a.real:
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = np.load(os.path.join(root, "tests", "golden", "policy_v1.npz")); c = np.load(os.path.join(root, "tests", "golden", "critic_v1.npz"))
+    blob = dd.PolicyBlob({k: torch.from_numpy(d[k]) for k in d.files if k.startswith("network")}, device=dev)
+    vblob = dd.ValueBlob({k: torch.from_numpy(c[k]) for k in c.files if k.startswith("network")}, device=dev)
+    env = dd.BatchedDroneEnv(n, device=dev, seed=0, randomize_drone=True, randomize_platform=True, max_steps=250, auto_reset=True)
+    env.reset()
+    pb = dd.policy_rollout(env, blob, T, want="arldo")
+    rew = pb["reward"]; val = dd.rollout_values(vblob, pb["obs"], env.observe().clone()); don = (pb["done"] != 0).to(torch.uint8)
+    print("real data: done rate %.4f, |value| mean %.1f, reward mean %.3f" % (don.float().mean().item(), val.abs().mean().item(), rew.mean().item()), file=sys.stderr)
 bufs = [torch.randn(T, n, device=dev, generator=g) for _ in range(4)]
 adv = torch.empty(T, n, device=dev); out2 = [torch.empty(T, n, device=dev) for _ in range(2)]
 mom = torch.zeros(3, dtype=torch.float64, device=dev)
