@@ -325,7 +325,7 @@ int dd_moments(const float* x, int64_t n, double* out, void* stream)
     if (n < 0) return DD_E_RANGE;
     if ((reinterpret_cast<uintptr_t>(x) & 3u) || (reinterpret_cast<uintptr_t>(out) & 7u)) return DD_E_ALIGN;
     if (n == 0) return 0;
-    const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 4, dd::kSMs * 4);    // 4 CTAs per SM: two atomics per CTA at the end
+    const int grid = dd::wave_grid(n / 4 + 1, dd::kRedBlock * 4, dd::kSMs * 8);    // (4 CTAs per SM measured slower: 16.7 vs 15 us at 16.4 M elements)
     dd::DeviceGuard guard((cudaStream_t)stream, x);
     if (guard.err != cudaSuccess) return (int)guard.err;
     return dd::launch_pdl(dd::moments_kernel, grid, dd::kRedBlock, (cudaStream_t)stream, x, n, out);
