@@ -64,7 +64,9 @@
 // takes off: LayerNorm pass 2 + conversions + A stores + last Linear 0.49 ms, the MMAs 0.26, the env step 0.20,
 // output stores 0.08, LayerNorm pass 1 0.02, the sampling Philox 0.00 -- the parts add up to the whole: a serial
 // chain per tile.  Tried and rejected this round: deferred outputs under the second MMA (+1 %), all four warps
-// waiting on the MMA mbarrier / suspend-time hints (+0.3..1.3 %), phase-shifted tile starts (0 %).
+// waiting on the MMA mbarrier / suspend-time hints (+0.3..1.3 %), phase-shifted tile starts (0 %), and a warp-specialised
+// rewrite (two tiles per warpgroup alternating phase by phase, MMA-issuer warps, mbarrier arrive instead of named barriers:
+// bit-identical, but 1.435 ms -- two compute warps per scheduler hide less than four; profiles/r02_k5b_experiment.cu.txt).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
