@@ -226,3 +226,32 @@ def test_prev_dist_is_invalidated_by_plain_steps():
     sa = torch.empty(6, n, device=DEV); sb = torch.empty(6, n, device=DEV)
     a.rollout(6, "bangbang", shaped_out=sa); b.rollout(6, "bangbang", shaped_out=sb)
     assert torch.equal(sa, sb)
+
+
+@pytest.mark.parametrize("S,C,L,dtype", [(1, 2, 3, torch.float32), (2, 5, 1, torch.float64), (5, 2, 2, torch.float64)])
+def test_sharded_edge_shapes(S, C, L, dtype):
+    """One shard with two chains requested, more chains than shards, a one-row trace, the float64 instantiation: the graph
+    path still equals eager stepping, and the captured pieces survive a set_trace() only for step_all."""
+    N = 300
+    kw = dict(KW, dtype=dtype)
+    g = dd.ShardedDroneEnv(S, N, device=DEV, chains=C, trace_len=L, **kw)
+    e = dd.ShardedDroneEnv(S, N, device=DEV, chains=C, trace_len=L, use_graphs=False, **kw)
+    assert g.C == min(C, S)
+    with pytest.raises(RuntimeError):
+        g.run(1)                                              # no trace yet
+    g.reset(); e.reset()
+    e.set_trace(g.random_trace().clone())
+    for k in (1, 2 * S * L + 1, 7):
+        g.run(k); e.run(k)
+    g.step_all(torch.zeros(S, N, dtype=torch.uint8, device=DEV)); e.step_all(torch.zeros(S, N, dtype=torch.uint8, device=DEV))
+    n_all = sum(1 for key in g._graphs if key[0] == "all")
+    g.set_trace(g.trace.clone())                               # drops the pieces captured over the old trace tensor only
+    assert sum(1 for key in g._graphs if key[0] == "run") == 0 and sum(1 for key in g._graphs if key[0] == "all") == n_all == 1
+    g.run(3); e.run(3)
+    g.join(); e.join()
+    for s in range(S):
+        _same_state(g.shards[s], e.shards[s])
+        assert torch.equal(g.shards[s].obs, e.shards[s].obs) and g.shards[s].obs.dtype == dtype
+    assert g.stats() == e.stats()
+    with pytest.raises(ValueError):
+        g.set_trace(torch.zeros(L + 1, S, N, dtype=torch.uint8, device=DEV))
