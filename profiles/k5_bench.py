@@ -20,12 +20,13 @@ dd = importlib.import_module("reinforcement-learning-101_b200")
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--envs", type=int, default=int(os.environ.get("K5_ENVS", 65536)))
     ap.add_argument("--T", type=int, default=250)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--want", default="arldo")
     ap.add_argument("--threshold", action="store_true")
     ap.add_argument("--operands", default="auto", choices=["auto", "bf16", "fp16"], help="16-bit format of the tensor-core operands")
+    ap.add_argument("--checksum", action="store_true", help="add sums of every output buffer and of the final env state")
     ap.add_argument("--values", action="store_true", help="also time critic values over the buffer, GAE, normalisation")
     args = ap.parse_args()
     dev = "cuda:0"
@@ -48,6 +49,9 @@ def main():
     out = {"kernel": "policy_rollout_kernel", "operands": blob.operand_dtype, "lib": os.environ.get("DRONE_B200_LIB", "default"), "envs": args.envs, "T": args.T, "want": args.want,
            "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
            "mlp_tflops": steps * 53376 / ms * 1e3 / 1e12, "stats": env.stats()}
+    if args.checksum:                                        # A/B runs of kernel variants: identical numbers <=> identical buffers
+        out["checksum"] = {k_: (float(v.double().sum()) if v.is_floating_point() else int(v.long().sum())) for k_, v in sorted(buf.items())}
+        out["checksum"]["state"] = float(sum(v.double().nan_to_num().sum() for v in env.get_state().values()))
     if args.values and "obs" in buf:
         # the critic over the whole rollout buffer + bootstrap row, then GAE and advantage normalisation
         c = np.load(os.path.join(ROOT, "tests", "golden", "critic_v1.npz"))

@@ -473,7 +473,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 
     // ---- my environment (FWD: my row of the current block, advanced in the loop) ----
     constexpr bool forward_only = FWD;
-    uint32_t tile0 = (blockIdx.x * kGroups + g) * kTile;
+    // FWD: consecutive tiles per CTA (walked block by block).  Rollout: tile b + gridDim.x * g in slot g of CTA b -- the
+    // launcher SPREADS the tiles over the SMs (policy_launch); a slot without a tile skips the step loop.
+    uint32_t tile0 = FWD ? (blockIdx.x * kGroups + g) * kTile : (blockIdx.x + gridDim.x * g) * kTile;
+    const int32_t T_mine = (FWD || tile0 < a.n) ? pa.T : 0;
     uint32_t i = tile0 + row;
     bool live = i < a.n;
     // FWD: a tile's [128][15] fp32 rows are contiguous: full 16-byte aligned tiles arrive by TMA into s_obs
@@ -523,7 +526,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                tempered = !FAST && pa.inv_temperature != 1.0f;
     const int32_t max_steps = a.max_steps;
     const bool obs_out = !forward_only && (FAST || pa.obs_tn != nullptr);
-    const bool obs_bulk = obs_out && tile0 + kTile <= a.n && (a.n & 3u) == 0u &&
+    // (a ragged last tile stores its live rows only: (n - tile0) * 60 bytes, a multiple of 16 when n % 4 == 0)
+    const uint32_t obs_bytes = (tile0 < a.n ? (a.n - tile0 < (uint32_t)kTile ? a.n - tile0 : (uint32_t)kTile) : 0u) * (kIn * 4u);
+    const bool obs_bulk = obs_out && tile0 < a.n && (a.n & 3u) == 0u &&
                           (reinterpret_cast<uintptr_t>(pa.obs_tn) & 15u) == 0u;
     float dprev = nan_of<float>(), dcur = dist * k.inv_width;
     if (live && shaping) dprev = a.prev_dist[i];
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         if (do_stats) stats_warp_commit(a.stats, pend.f_stat, pend.ret_stat, pend.len_stat);
     };
 
-    for (int32_t t = 0; t < pa.T; ++t) {
+    for (int32_t t = 0; t < T_mine; ++t) {
         const size_t o = FWD ? (size_t)i : (size_t)t * a.n + i;
         // ---------------- observation -> A0 (bf16, K = 16: 15 inputs + constant 1 for the bias) -------
         DD_TRACE(0);                                         // step start
@@ -622,7 +627,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             tc_fence_after();
             if (obs_bulk) {                                  // the staged observation tile is complete: one TMA store
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(pa.obs_tn + ((size_t)t * a.n + tile0) * kIn), "r"(smem_u32(s_obs)), "n"(kObsTileBytes) : "memory");
+                             :: "l"(pa.obs_tn + ((size_t)t * a.n + tile0) * kIn), "r"(smem_u32(s_obs)), "r"(obs_bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
 #pragma unroll
@@ -765,7 +770,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         pend.p0 = p0; pend.p1 = p1; pend.p2 = p2; pend.act = act; pend.reward = reward; pend.shaped = shaped;
         pend.oflags = oflags; pend.f_stat = f_stat; pend.ret_stat = ret_stat; pend.len_stat = len_stat;
     }
-    if (!forward_only && pa.T > 0) flush_pending((size_t)(pa.T - 1) * a.n + i);
+    if (!forward_only && T_mine > 0) flush_pending((size_t)(T_mine - 1) * a.n + i);
 
     if (live && !forward_only) {
         store4(a.pos_vel, i, e.x, e.y, e.vx, e.vy);
@@ -924,6 +929,16 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
         grid = blocks < sms ? blocks : sms;                 // persistent: one CTA per SM walks the row blocks
         pa.T = (blocks + grid - 1) / grid;
     } else {
+        // Per-SM throughput saturates with the number of resident tiles -- measured on B200 with every SM busy: 0.77 / 0.91 /
+        // 1.08 / 1.26 ms per 250 steps at 1 / 2 / 3 / 4 tiles per SM -- so up to 3 tiles per SM the tiles are SPREAD over the
+        // SMs (tile b + grid * g in slot g of CTA b: a 32,768-env batch runs 2 tiles on each of 128 SMs instead of 4 on 64),
+        // and above that they are packed four to a CTA (cfg 4, 512 tiles: 128 CTAs x 4 at 1.22 ms; 68 CTAs x 4 + 80 x 3 on all
+        // 148 SMs measured 1.26 -- the SMs with four tiles set the time and the busier chip clocks lower).
+        int sms = 0;
+        const cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, guard.dev);
+        if (e != cudaSuccess) return (int)e;
+        const int64_t tiles = (n + kTile - 1) / kTile;
+        if (tiles <= 3ll * sms) grid = (int)(tiles < sms ? tiles : sms);
         const bool fast = pa.mode == DD_ACTION_SAMPLE && pa.inv_temperature == 1.0f && pa.auto_reset && pa.a.stats &&
                           pa.actions_tn && pa.logp_tn && pa.reward_tn && pa.done_tn && pa.obs_tn && !pa.shaped_tn && !pa.probs_tn;
 #define DD_K5(DEF_, FAST_) (f16 ? policy_rollout_kernel<DEF_, kChunk, false, 3, FAST_, true> : policy_rollout_kernel<DEF_, kChunk, false, 3, FAST_, false>)
