@@ -67,6 +67,11 @@
 // waiting on the MMA mbarrier / suspend-time hints (+0.3..1.3 %), phase-shifted tile starts (0 %), and a warp-specialised
 // rewrite (two tiles per warpgroup alternating phase by phase, MMA-issuer warps, mbarrier arrive instead of named barriers:
 // bit-identical, but 1.435 ms -- two compute warps per scheduler hide less than four; profiles/r02_k5b_experiment.cu.txt).
+// Later (profiles/r02_k5_experiments_session3.json): half-N MMA batches to start pass 1 early (+8.5 %: an SS-form K-block
+// streams its 4 KB A block through the 128 B/clk shared-memory port whatever N is -- that port, ~170 KB per tile-step, is a
+// co-limiter), and dynamic (tile, segment) work units over all 148 SMs (bit-identical, no gain on cfg 4: with the whole chip
+// busy T(k) = 0.77 / 0.91 / 1.08 / 1.26 ms, so a 3 / 4 mix is bounded at 1.17 ms and the hand-offs eat it).  Kept from that
+// work: the launcher spreads the tiles over the SMs up to 3 per SM (policy_launch).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
