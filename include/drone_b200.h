@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DD_ABI_VERSION 4
+#define DD_ABI_VERSION 5
 
 /* ---- flag byte (per-step output and persistent state) ---------------------- */
 #define DD_DONE        0x01u   /* game_engine.py:53  self.done            */
@@ -314,6 +314,12 @@ int dd_policy_rollout(const DDState *s, const DDParams *p, const DDEnvConfig *c,
                       const DDPolicyConsts *consts, int32_t mode, float temperature, uint32_t t0, int32_t T, uint8_t *actions_tn, float *logp_tn, float *reward_tn,
                       uint8_t *done_tn, float *obs_tn, float *probs_tn, float *shaped_tn, uint64_t *stats, int64_t n,
                       void *stream);
+
+/* Launch shape of dd_policy_rollout (pure host function; what the launcher itself uses): the number of CTAs for n envs on
+ * a device with `sms` SMs.  Slot g (0..3) of CTA b runs the tile of 128 envs number b + grid * g (if it exists).  Up to 3
+ * tiles per SM the tiles are spread over the SMs, above that packed four to a CTA (per-SM throughput saturates with the
+ * resident tiles).  0 for n outside (0, DD_MAX_ENVS_PER_CALL]. */
+int dd_policy_rollout_grid(int64_t n, int32_t sms);
 
 #ifdef __cplusplus
 }

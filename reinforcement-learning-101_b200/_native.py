@@ -27,7 +27,7 @@ HOST_TWIN_SOURCE = "host_twin.cpp"
 HOST_TWIN_FLAGS = ("-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared")
 
 # ---- constants of include/drone_b200.h ------------------------------------------------------
-ABI_VERSION = 4
+ABI_VERSION = 5
 DONE, LANDED, CRASHED, TRUNCATED = 0x01, 0x02, 0x04, 0x08
 CAUSE_MASK, CAUSE_GROUND, CAUSE_FUEL, CAUSE_OOB = 0x30, 0x10, 0x20, 0x30
 ACT_MAIN, ACT_LEFT, ACT_RIGHT, ACT_SKIP = 0x01, 0x02, 0x04, 0x80
@@ -197,6 +197,8 @@ def lib():
     L.dd_value_forward.argtypes = [vp, C.POINTER(DDPolicyConsts), vp, vp, i64, vp]
     L.dd_policy_rollout.restype = C.c_int
     L.dd_policy_rollout.argtypes = [PS, PP, PC, vp, C.POINTER(DDPolicyConsts), i32, C.c_float, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.dd_policy_rollout_grid.restype = C.c_int
+    L.dd_policy_rollout_grid.argtypes = [i64, i32]
     if L.dd_abi_version() != ABI_VERSION:
         raise NativeError(f"libdrone_b200.so ABI {L.dd_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L
@@ -219,6 +221,6 @@ EXPORTS = (
     "dd_abi_version", "dd_default_params", "dd_error_string", "dd_reset", "dd_step", "dd_step_plan", "dd_step_planned",
     "dd_rollout", "dd_rollout_shaped",
     "dd_fill_random_actions", "dd_pack_actions", "dd_stats_collapse", "dd_moments", "dd_normalize", "dd_gae", "dd_gae_moments",
-    "dd_policy_pack", "dd_policy_pack_ex", "dd_policy_forward", "dd_policy_rollout", "dd_value_pack", "dd_value_forward", "dd_gather_env", "dd_discounted_returns",
+    "dd_policy_pack", "dd_policy_pack_ex", "dd_policy_forward", "dd_policy_rollout", "dd_policy_rollout_grid", "dd_value_pack", "dd_value_forward", "dd_gather_env", "dd_discounted_returns",
 )
 HOST_TWIN_EXPORTS = ("dd_host_abi_version", "dd_reset_host", "dd_step_host", "dd_rollout_host")

@@ -916,6 +916,19 @@ static bool pol_params_default(const DDParams& p)
     return memcmp(&p, &d, sizeof d) == 0;
 }
 
+// CTAs of a rollout launch over n envs on a device with `sms` SMs; slot g (0..3) of CTA b runs tile b + grid * g.
+// Per-SM throughput saturates with the number of resident tiles -- measured on B200 with every SM busy: 0.77 / 0.91 /
+// 1.08 / 1.26 ms per 250 steps at 1 / 2 / 3 / 4 tiles per SM -- so up to 3 tiles per SM the tiles are SPREAD over the
+// SMs (a 32,768-env batch runs 2 tiles on each of 128 SMs instead of 4 on 64), and above that they are packed four to
+// a CTA (cfg 4, 512 tiles: 128 CTAs x 4 at 1.22 ms; 68 CTAs x 4 + 80 x 3 on all 148 SMs measured 1.26 -- the SMs with
+// four tiles set the time and the busier chip clocks lower).
+static int rollout_grid(int64_t n, int sms)
+{
+    const int64_t tiles = (n + kTile - 1) / kTile, blocks = (tiles + kGroups - 1) / kGroups;
+    if (sms > 0 && tiles <= (int64_t)(kGroups - 1) * sms) return (int)(tiles < sms ? tiles : sms);
+    return (int)blocks;
+}
+
 static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, cudaStream_t st)
 {
     const int blocks = (int)((n + kTile * kGroups - 1) / (kTile * kGroups));
@@ -934,16 +947,10 @@ static int policy_launch(PArgs& pa, const DDParams& p, int64_t n, bool forward, 
         grid = blocks < sms ? blocks : sms;                 // persistent: one CTA per SM walks the row blocks
         pa.T = (blocks + grid - 1) / grid;
     } else {
-        // Per-SM throughput saturates with the number of resident tiles -- measured on B200 with every SM busy: 0.77 / 0.91 /
-        // 1.08 / 1.26 ms per 250 steps at 1 / 2 / 3 / 4 tiles per SM -- so up to 3 tiles per SM the tiles are SPREAD over the
-        // SMs (tile b + grid * g in slot g of CTA b: a 32,768-env batch runs 2 tiles on each of 128 SMs instead of 4 on 64),
-        // and above that they are packed four to a CTA (cfg 4, 512 tiles: 128 CTAs x 4 at 1.22 ms; 68 CTAs x 4 + 80 x 3 on all
-        // 148 SMs measured 1.26 -- the SMs with four tiles set the time and the busier chip clocks lower).
         int sms = 0;
         const cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, guard.dev);
         if (e != cudaSuccess) return (int)e;
-        const int64_t tiles = (n + kTile - 1) / kTile;
-        if (tiles <= 3ll * sms) grid = (int)(tiles < sms ? tiles : sms);
+        grid = rollout_grid(n, sms);
         const bool fast = pa.mode == DD_ACTION_SAMPLE && pa.inv_temperature == 1.0f && pa.auto_reset && pa.a.stats &&
                           pa.actions_tn && pa.logp_tn && pa.reward_tn && pa.done_tn && pa.obs_tn && !pa.shaped_tn && !pa.probs_tn;
 #define DD_K5(DEF_, FAST_) (f16 ? policy_rollout_kernel<DEF_, kChunk, false, 3, FAST_, true> : policy_rollout_kernel<DEF_, kChunk, false, 3, FAST_, false>)
@@ -1024,6 +1031,12 @@ int dd_policy_forward(const void* blob, const DDPolicyConsts* consts, const floa
 int dd_value_forward(const void* blob, const DDPolicyConsts* consts, const float* obs, float* values, int64_t n, void* stream)
 {
     return dd::forward_common(blob, consts, obs, values, 1, n, stream);
+}
+
+int dd_policy_rollout_grid(int64_t n, int32_t sms)
+{
+    if (n <= 0 || n > (int64_t)DD_MAX_ENVS_PER_CALL) return 0;
+    return dd::rollout_grid(n, sms);
 }
 
 int dd_policy_rollout(const DDState* s, const DDParams* p, const DDEnvConfig* c, const void* blob,

@@ -121,6 +121,33 @@ def test_missing_library_fails_loudly(tmp_path):
     assert "RAISED" in out.stdout, out.stderr
 
 
+def test_policy_rollout_grid_covers_every_tile_once(lib):
+    """Launch shape of dd_policy_rollout (host function): slot g of CTA b runs tile b + grid * g.  Every tile has exactly
+    one slot; up to 3 tiles per SM the tiles are spread (never more than ceil(tiles / sms) on a CTA while SMs idle),
+    above that packed four to a CTA (the measured optimum for BASELINE configs[3])."""
+    sms = 148
+    for n in (1, 127, 128, 129, 1000, 4096, 148 * 128, 148 * 128 + 1, 32768, 50000, 148 * 3 * 128, 148 * 3 * 128 + 1, 60000, 65536,
+              148 * 4 * 128, 148 * 4 * 128 + 1, 131072, 1 << 20):
+        tiles = -(-n // 128)
+        grid = lib.dd_policy_rollout_grid(n, sms)
+        assert grid >= 1
+        owners = {}
+        for b in range(grid):
+            for g in range(4):
+                t = b + grid * g
+                if t < tiles:
+                    assert t not in owners
+                    owners[t] = b
+        assert len(owners) == tiles, (n, grid)
+        per_cta = max(sum(1 for v in owners.values() if v == b) for b in range(min(grid, 200)))
+        if tiles <= 3 * sms:
+            assert grid == min(tiles, sms) and per_cta == -(-tiles // grid) <= 3
+        else:
+            assert grid == -(-tiles // 4) and per_cta == 4
+    assert lib.dd_policy_rollout_grid(65536, sms) == 128 and lib.dd_policy_rollout_grid(32768, sms) == 148
+    assert lib.dd_policy_rollout_grid(0, sms) == 0 and lib.dd_policy_rollout_grid(-5, sms) == 0
+
+
 def test_shard_range_covers_all_ids():
     for total, ws in ((16, 1), (16, 8), (17, 4), (3, 8), (1 << 24, 8)):
         spans = [dd.shard_range(total, r, ws) for r in range(ws)]
