@@ -248,7 +248,7 @@ typedef struct DDPolicy {
     const float *w3, *b3;                 /* network.9 (Linear 64->3) */
 } DDPolicy;
 
-#define DD_POLICY_BLOB_BYTES 65568        /* device workspace filled by dd_policy_pack */
+#define DD_POLICY_BLOB_BYTES 67616        /* device workspace filled by dd_policy_pack */
 #define DD_ACTION_THRESHOLD 0             /* action = probs > 0.5        (c18:L24-25) */
 #define DD_ACTION_SAMPLE    1             /* action ~ Bernoulli(probs)   (c16:L61-63), Philox */
 

@@ -100,10 +100,12 @@ constexpr int kW1bOff = kW1Off + kH2 * kH1 * 2;            // [128][16]  col 0/1
 constexpr int kW2Off = kW1bOff + kH2 * 16 * 2;             // [64][128]  G2 C2 W2
 constexpr int kW2bOff = kW2Off + kH3 * kH2 * 2;            // [64][16]   col 0/1 = hi/lo of G2 C2 b2
 constexpr int kW0loOff = kW2bOff + kH3 * 16 * 2;           // [128][16]  low halves of the layer-0 image (split bf16)
-constexpr int kParOff = kW0loOff + kH1 * kInPad * 2;       // a DDPolicyConsts image (fp32 parameters + operand format)
+constexpr int kW3Off = kW0loOff + kH1 * kInPad * 2;        // [16][64]   the last Linear x |gamma2| for the tensor-core head: rows 0-2 = hi, 3-5 = lo, rest 0
+constexpr int kW3Rows = 16;                                // UMMA N of the head MMA (the smallest N at M = 128)
+constexpr int kParOff = kW3Off + kW3Rows * kH3 * 2;        // a DDPolicyConsts image (fp32 parameters + operand format)
 // word offsets inside it: beta / |gamma| per LayerNorm, then the last Linear (x |gamma| of the last LayerNorm), format
 constexpr int pBe0 = 0, pBe1 = 128, pBe2 = 256, pW3 = 320, pB3 = 512, pFmt = 516, kParWords = 520;
-constexpr int kBlobBytes = kParOff + kParWords * 4;        // 65,568
+constexpr int kBlobBytes = kParOff + kParWords * 4;        // 67,616
 static_assert(kBlobBytes == DD_POLICY_BLOB_BYTES, "header and kernel disagree on the blob size");
 static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of uint4");
 static_assert(sizeof(DDPolicyConsts) == kParWords * 4, "the blob's parameter section is a DDPolicyConsts image");
@@ -123,6 +125,12 @@ constexpr float kGammaFloor = 1e-12f;                      // |gamma| below this
 #ifndef DD_K5_ABLATE
 #define DD_K5_ABLATE 0                         // profiling only (wrong results): 1 no MMA issue, 2 no env step, 4 no Philox,
 #endif                                         //   8 no output stores / obs staging, 16 no LayerNorm pass 1, 32 no pass 2, 64 / 128 one beta / w3 constant for all columns
+#ifndef DD_K5_MMA_HEAD
+#define DD_K5_MMA_HEAD 1                       // policy head (64 -> 3) as a fourth tcgen05.mma (TS form) instead of 96 FFMA2 + 64 FMNMX + 48 LDCU per env-step
+#endif
+#ifndef DD_K5_FLUSH_AT
+#define DD_K5_FLUSH_AT 1                       // which MMA shadow hosts the previous step's deferred outputs (1 or 3)
+#endif
 constexpr int kChunk = DD_K5_CHUNK;                        // accumulator columns per tcgen05.ld (8, 16 or 32; 16 measured best)
 
 constexpr int kABytes = kTile * kH1 * 2;                   // 32 KB: A tile of one group (A0 aliases its head)
@@ -204,6 +212,8 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "n"(kTile) : "memory"); }
+// (In front of an MMA issue only the issuing warp has to wait; `bar.arrive` for the other three measured no different: the
+// MMA cannot start before the last warp has arrived either way.)
 // Wait for the tile's committed MMAs.  (Round 2 measured the alternatives on B200 -- all four warps waiting on the
 // mbarrier, with and without a suspend-time hint: 1.265 / 1.278 ms against 1.262 for this scheme.)  Only the issuing warp polls the mbarrier (try_wait returns after a short
 // system-defined time, so a waiting warp keeps executing a poll loop that competes for issue slots: ~200
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     const uint32_t a_addr = smem_u32(s_a);
     const uint32_t w0_addr = smem_u32(s_blob + kW0Off), w1_addr = smem_u32(s_blob + kW1Off), w2_addr = smem_u32(s_blob + kW2Off);
     const uint32_t w1b_addr = smem_u32(s_blob + kW1bOff), w2b_addr = smem_u32(s_blob + kW2bOff), ones_addr = smem_u32(smem + kSmemOnes);
-    const uint32_t w0lo_addr = smem_u32(s_blob + kW0loOff);
+    const uint32_t w0lo_addr = smem_u32(s_blob + kW0loOff), w3_addr = smem_u32(s_blob + kW3Off);
     uint32_t phase = 0;
     float* s_obs = reinterpret_cast<float*>(smem + kSmemObs + g * kObsTileBytes);
     const DDPolicyConsts& pc = pa.pc;
@@ -619,7 +629,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
 #pragma unroll
             for (int j = 0; j < kIn; ++j) dst[j] = ob[j];
         }
-        if (!forward_only && t > 0) flush_pending(o - a.n);   // (under the second MMA instead: measured slower, 1.270 vs 1.257 ms)
+        if (DD_K5_FLUSH_AT == 1 && !forward_only && t > 0) flush_pending(o - a.n);   // (under the second MMA instead: measured slower, 1.270 vs 1.257 ms)
         DD_TRACE(3);                                         // shadow work 1 done
         wait_mma(bar, phase, issuer_warp, g);
         DD_TRACE(4);                                         // MMA1 done
@@ -691,11 +701,41 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             umma_commit(bar);
         }
 #endif
-        float s_pre = 0.f, c_pre = 1.f;                      // under the third MMA: sin / cos of the pre-update angle
-        if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }   // (main thrust, drone.py:58-66)
+        constexpr bool mma_head = DD_K5_MMA_HEAD && DD_K5_TS_LAYER3 && HEAD == 3;
+        float s_pre = 0.f, c_pre = 1.f;                      // under the third MMA (the fourth with the tensor-core head): sin / cos of the pre-update angle
+        if (!forward_only && !mma_head) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }   // (main thrust, drone.py:58-66)
+        if (DD_K5_FLUSH_AT == 3 && !forward_only && t > 0) flush_pending(o - a.n);
         DD_TRACE(9);                                         // shadow work 3 done
         wait_mma(bar, phase, issuer_warp, g);
         DD_TRACE(10);                                        // MMA3 done
+        float z0, z1, z2;
+        if constexpr (mma_head) {
+            // ---------------- epilogue 3, then the policy head as a fourth MMA ----------------------------------
+            // The activations of the last hidden layer go to TMEM like those of layer 2 (packed 16-bit, ReLU inside the
+            // conversion) into columns [0, 32) -- A2 is dead once MMA3 has completed --, the head D4[128 x 16] = A3 x W3''^T
+            // accumulates in columns [32, 48): image rows 0-2 hold the high halves of w3 |gamma2|, rows 3-5 the low halves, so
+            // logit_o = D4[o] + D4[3 + o] + b3[o] carries only the rounding of the activations.  That replaces 96 FFMA2 + 64
+            // FMNMX + 48 LDCU per env-step (15 % of the kernel's instructions) with one more hand-off.
+            ln_epilogue<kH3, CH>(trow + 64u, pc.beta2, [&](int c, const float (&y)[CH]) { store_a_chunk_relu_tmem<CH, F16>(trow, c, y); });
+            tmem_st_wait();
+            tc_fence_before(); group_bar(g);
+            if (issuer_warp && elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < kH3 / 16; ++j)
+                    umma_ts(tmem_d + 32u, tmem_d + (uint32_t)(8 * j),
+                            umma_desc(w3_addr + j * 2 * (kW3Rows * 16), kW3Rows * 16, 128), umma_idesc(128, kW3Rows, F16), j > 0 ? 1u : 0u);
+                umma_commit(bar);
+            }
+            if (!forward_only) { Arith<float>::sincos_deg(e.angle, s_pre, c_pre); pin(s_pre); pin(c_pre); }   // under the head MMA
+            wait_mma(bar, phase, issuer_warp, g);             // (sin / cos under MMA3 instead, or all four warps on the mbarrier: measured equal or slower)
+            TmemChunk<8> d4;
+            d4.issue(trow + 32u);
+            d4.wait();
+            z0 = (__uint_as_float(d4.r[0]) + __uint_as_float(d4.r[3])) + pc.b3[0];
+            z1 = (__uint_as_float(d4.r[1]) + __uint_as_float(d4.r[4])) + pc.b3[1];
+            z2 = (__uint_as_float(d4.r[2]) + __uint_as_float(d4.r[5])) + pc.b3[2];
+        } else {
         // ---------------- epilogue 3 + layer 4 (64 -> 3) on the CUDA cores ------------------------------
         float2 za = make_float2(0.f, 0.f), zb = za, zc = za;
         ln_epilogue<kH3, CH>(trow + (DD_K5_TS_LAYER3 ? 64u : 0u), pc.beta2, [&](int c, const float (&y)[CH]) {
@@ -711,7 +751,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                 }
             }
         });
-        const float z0 = za.x + za.y + pc.b3[0], z1 = zb.x + zb.y + pc.b3[1], z2 = zc.x + zc.y + pc.b3[2];
+        z0 = za.x + za.y + pc.b3[0]; z1 = zb.x + zb.y + pc.b3[1]; z2 = zc.x + zc.y + pc.b3[2];
+        }
         DD_TRACE(11);                                        // epilogue 3 + last Linear done
         tc_fence_before();                                   // my TMEM reads are done before the next MMA may overwrite
         // sigmoid with the approximate reciprocal (MUFU.RCP, ~1 ulp): the IEEE division sequence costs ~8 issue slots
@@ -857,12 +898,12 @@ __device__ void pack_write_images(const PackLayer (&Ls)[3], const float (*mean)[
 __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, int head, int operands, uint8_t* blob)
 {
     __shared__ float s_mean[3][129];                       // per layer: column means over the outputs; [K] = mean of the bias
-    __shared__ unsigned s_imax[3], s_bmax, s_gmin, s_gmax;  // maxima / minima as the bit patterns of non-negative floats
+    __shared__ unsigned s_imax[3], s_bmax, s_gmin, s_gmax, s_w3max;  // maxima / minima as the bit patterns of non-negative floats
     __shared__ int s_fmt;
     const int tid = threadIdx.x, nth = blockDim.x;
     const PackLayer Ls[3] = {{p.w0, p.b0, p.g0, nullptr, kH1, kIn}, {p.w1, p.b1, p.g1, p.g0, kH2, kH1}, {p.w2, p.b2, p.g2, p.g1, kH3, kH2}};
     if (tid < 3) s_imax[tid] = 0u;
-    if (tid == 0) { s_bmax = 0u; s_gmin = 0x7f800000u; s_gmax = 0u; }
+    if (tid == 0) { s_bmax = 0u; s_gmin = 0x7f800000u; s_gmax = 0u; s_w3max = 0u; }
     for (int l = 0; l < 3; ++l) {
         const PackLayer& L = Ls[l];
         for (int kk = tid; kk <= L.K; kk += nth) {
@@ -889,9 +930,13 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, int head, 
             atomicMax(&s_bmax, bp == bp ? __float_as_uint(bp) : 0x7f800000u);
         }
     }
+    for (int j = tid; j < head * kH3; j += nth) {            // the head image (tensor-core head): |w3 gamma2| must not overflow fp16
+        const float v = fabsf(p.w3[j] * gamma_abs(p.g2[j % kH3]));
+        atomicMax(&s_w3max, v == v ? __float_as_uint(v) : 0x7f800000u);
+    }
     __syncthreads();
     if (tid == 0) {
-        bool ok = __uint_as_float(s_gmin) >= 0.015625f && __uint_as_float(s_gmax) <= 64.f && __uint_as_float(s_bmax) <= 1024.f;
+        bool ok = __uint_as_float(s_w3max) <= 1024.f && __uint_as_float(s_gmin) >= 0.015625f && __uint_as_float(s_gmax) <= 64.f && __uint_as_float(s_bmax) <= 1024.f;
         for (int l = 0; l < 3; ++l) ok = ok && __uint_as_float(s_imax[l]) <= 1024.f && __uint_as_float(s_imax[l]) >= 0.00390625f;
         s_fmt = (operands != DD_OPERANDS_BF16 && ok) ? DD_OPERANDS_FP16 : DD_OPERANDS_BF16;
     }
@@ -899,6 +944,18 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(DDPolicy p, int head, 
     if (s_fmt == DD_OPERANDS_FP16) pack_write_images<true>(Ls, s_mean, blob, tid, nth);
     else pack_write_images<false>(Ls, s_mean, blob, tid, nth);
 
+    // the head image [16][64] for the tensor-core head: row o = hi, row 3 + o = lo of w3[o][k] |gamma2[k]|, the other rows 0
+    for (int j = tid; j < kW3Rows * kH3; j += nth) {
+        const int n = j / kH3, kk = j % kH3, o = n % 3;
+        float v = 0.f;
+        if (n < 6 && o < head) {
+            const float w = p.w3[o * kH3 + kk] * gamma_abs(p.g2[kk]);
+            const float hi = s_fmt == DD_OPERANDS_FP16 ? round16<true>(w) : round16<false>(w);
+            v = n < 3 ? w : w - hi;
+        }
+        if (s_fmt == DD_OPERANDS_FP16) store16<true>(blob + kW3Off, img_at(kW3Rows, n, kk), v);
+        else store16<false>(blob + kW3Off, img_at(kW3Rows, n, kk), v);
+    }
     float* par = reinterpret_cast<float*>(blob + kParOff);
     for (int j = tid; j < 128; j += nth) {
         par[pBe0 + j] = p.be0[j] / gamma_abs(p.g0[j]);

@@ -18,7 +18,7 @@ import torch
 from . import _native as nv
 from .env import BatchedDroneEnv
 
-BLOB_BYTES = 65568
+BLOB_BYTES = 67616
 _OPERANDS = {"auto": nv.OPERANDS_AUTO, "bf16": nv.OPERANDS_BF16, "fp16": nv.OPERANDS_FP16}
 ACTION_THRESHOLD, ACTION_SAMPLE = 0, 1
 _KEYS = ("network.0.weight", "network.0.bias", "network.1.weight", "network.1.bias",
@@ -30,7 +30,7 @@ _SHAPES = ((128, 15), (128,), (128,), (128,), (128, 128), (128,), (128,), (128,)
 
 
 class PolicyBlob:
-    """Device-resident packed network (65,568 bytes) + its host-side per-column constants.
+    """Device-resident packed network (67,616 bytes) + its host-side per-column constants.
     ``head=3``: the policy ``DroneGamerBoi`` (sigmoid probabilities); ``head=1``: the critic
     ``DroneTeacherBoi`` (same trunk, ``Linear(64, 1)``, raw scalar) -- see ``ValueBlob``."""
 
