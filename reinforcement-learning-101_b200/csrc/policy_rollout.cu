@@ -36,12 +36,15 @@
 //   * each thread reads its accumulator row with `tcgen05.ld.32x32b.x16` (SASS LDTM), twice,
 //     double-buffered (chunk c+1 is in flight while chunk c is processed) and writes the next A tile
 //     straight into the UMMA layout;
-//   * the operand images (bf16, already in UMMA layout; 62 KB) + the ones block (4 KB) live in shared
+//   * the operand images (16-bit, already in UMMA layout; 64 KB with the head image) + the ones block (4 KB) live in shared
 //     memory for the whole kernel, the A tiles take 32 KB per tile, the observation staging tiles
 //     (one TMA bulk store per tile-step) 7.5 KB per tile: 224 KB of the 227 KB;
-//   * the last layer (64 -> 3) and the sigmoid / Bernoulli / log-prob are folded into the third
-//     epilogue on the CUDA cores; the environment step is `step_core` from drone_core.cuh, the
-//     same code as K1, so the environment side is bit-identical to dd_rollout on the same actions.
+//   * the policy head (64 -> 3) is a FOURTH tcgen05.mma (TS form, N = 16: rows 0-2 / 3-5 of its image are the high / low
+//     halves of w3 |gamma2|) fed from TMEM by the third epilogue -- the 96 FFMA2 + 64 FMNMX + 44 LDCU per env-step it took
+//     on the CUDA cores cost more than the extra hand-off (1.220 -> 1.176 ms); the critic's one-row head (forward-only
+//     instantiation) stays on the CUDA cores in fp32.  Sigmoid / Bernoulli / log-prob follow on the CUDA cores; the
+//     environment step is `step_core` from drone_core.cuh, the same code as K1, so the environment side is bit-identical
+//     to dd_rollout on the same actions.
 //   * layer 3 takes its A operand from TENSOR memory (tcgen05.mma "TS" form): the second epilogue writes the packed
 //     16-bit activations with tcgen05.st into columns [0, 64) of its own accumulator -- columns pass 2 has already
 //     consumed -- and D3 accumulates in columns [64, 128).  That takes the 32 KB A2 store and the 32 KB A2 operand read
@@ -55,10 +58,11 @@
 //     edge (step_core<.., PRE_SC>: same decisions bit for bit): 1.250 -> 1.220 ms.
 // The four tiles of a CTA are independent pipelines, so while one waits for its MMAs the other three
 // keep the CUDA cores busy; work that is not on the chain obs -> network -> action -> env step -> obs runs in
-// the shadow of an MMA, where the warp would otherwise sleep: the previous step's log-prob / output stores /
-// statistics under the first, the Philox draws under the second, sin / cos of the pre-update angle under the
-// third.  Measured on B200, cfg 4 (profiles/r02_k5_ablation.json): 1.22 ms per 65,536 x 250 launch,
-// 1,445 instructions per env-step, issue slots 64 % busy, tensor pipe 47 %.  T(k tiles per SM) = 0.72 / 0.86 / 1.02 /
+// the shadow of an MMA, where the warp would otherwise sleep: the previous step's log-prob / output stores
+// under the first, the Philox draws under the second, sin / cos of the pre-update angle under the head MMA; the episode
+// statistics are accumulated per thread and committed once per rollout.  Measured on B200, cfg 4 (DESIGN.md 4b,
+// profiles/r02b_ncu_policy_rollout_summary.txt): 1.155 ms per 65,536 x 250 launch, 1,300 instructions per env-step, issue
+// slots 63 % busy, tensor pipe 53 %.  Before the tensor-core head (1.22 ms, 1,445 instructions, 64 % / 47 %):  T(k tiles per SM) = 0.72 / 0.86 / 1.02 /
 // 1.26 ms: one tile alone needs 5,500 cycles per step (its chain: 3 x {fence, barrier, MMA, mbarrier, TMEM read,
 // two-pass LayerNorm}, sample, env step), four tiles overlap to 9,300.  Removing one part at a time (timing only)
 // takes off: LayerNorm pass 2 + conversions + A stores + last Linear 0.49 ms, the MMAs 0.26, the env step 0.20,
