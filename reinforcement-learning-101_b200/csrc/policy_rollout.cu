@@ -379,8 +379,10 @@ __device__ __forceinline__ void ln_epilogue(uint32_t trow, const float (&beta)[N
         }
     }
     }
-    const float sq = ((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y));
-    const float rstd = rsqrtf(fmaf(sq, 1.0f / N, 1e-5f));                  // biased variance, like nn.LayerNorm
+    const float2 qs = __fadd2_rn(__fadd2_rn(q[0], q[1]), __fadd2_rn(q[2], q[3]));     // packed adds: 4 instructions instead of 7
+    const float sq = qs.x + qs.y;
+    float rstd;                                                            // biased variance, like nn.LayerNorm; the argument is
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd) : "f"(fmaf(sq, 1.0f / N, 1e-5f)));   //   >= 1e-5: one MUFU.RSQ, no denormal fix-up
     const float2 r2 = make_float2(rstd, rstd);
     if (DD_K5_ABLATE & 32) { buf[0].wait(); return; }
 #pragma unroll
@@ -571,8 +573,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                 const float eps = 1.1920929e-07f;
                 const float q0 = fminf(fmaxf(pend.p0, eps), 1.f - eps), q1 = fminf(fmaxf(pend.p1, eps), 1.f - eps),
                             q2 = fminf(fmaxf(pend.p2, eps), 1.f - eps);
-                pa.logp_tn[o_prev] = __logf((pend.act & DD_ACT_MAIN) ? q0 : 1.f - q0) + __logf((pend.act & DD_ACT_LEFT) ? q1 : 1.f - q1) +
-                                     __logf((pend.act & DD_ACT_RIGHT) ? q2 : 1.f - q2);
+                // one logarithm of the product (each factor >= 1.19e-7: no underflow) instead of three
+                pa.logp_tn[o_prev] = __logf((((pend.act & DD_ACT_MAIN) ? q0 : 1.f - q0) * ((pend.act & DD_ACT_LEFT) ? q1 : 1.f - q1)) *
+                                            ((pend.act & DD_ACT_RIGHT) ? q2 : 1.f - q2));
             }
             if (out_rew) pa.reward_tn[o_prev] = pend.reward;
             if (out_done) pa.done_tn[o_prev] = (uint8_t)pend.oflags;
@@ -611,8 +614,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             for (int j = 0; j < 4; ++j) {
                 const float x0 = ob[8 * q + 2 * j], x1 = ob[8 * q + 2 * j + 1];
                 hi[j] = pack16<F16>(x0, x1);
+                // rollout: inputs 13, 14 (landed, crashed) are exactly 0 or 1 and input 15 is the constant 1: no low halves
+                if (!FWD && q == 1 && j == 3) { lo[j] = 0u; continue; }
                 const float2 h = unpack16<F16>(hi[j]);
-                lo[j] = pack16<F16>(x0 - h.x, x1 - h.y);
+                lo[j] = (!FWD && q == 1 && j == 2) ? pack16<F16>(x0 - h.x, 0.f) : pack16<F16>(x0 - h.x, x1 - h.y);
             }
             *reinterpret_cast<uint4*>(s_a + q * (kTile * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(s_a + (2 + q) * (kTile * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
