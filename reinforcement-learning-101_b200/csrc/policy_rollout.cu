@@ -61,7 +61,7 @@
 // the shadow of an MMA, where the warp would otherwise sleep: the previous step's log-prob / output stores
 // under the first, the Philox draws under the second, sin / cos of the pre-update angle under the head MMA; the episode
 // statistics are accumulated per thread and committed once per rollout.  Measured on B200, cfg 4 (DESIGN.md 4b,
-// profiles/r02b_ncu_policy_rollout_summary.txt): 1.155 ms per 65,536 x 250 launch, 1,300 instructions per env-step, issue
+// profiles/r02b_ncu_policy_rollout_summary.txt): 1.134 ms per 65,536 x 250 launch, 1,266 instructions per env-step, issue
 // slots 63 % busy, tensor pipe 53 %.  Before the tensor-core head (1.22 ms, 1,445 instructions, 64 % / 47 %):  T(k tiles per SM) = 0.72 / 0.86 / 1.02 /
 // 1.26 ms: one tile alone needs 5,500 cycles per step (its chain: 3 x {fence, barrier, MMA, mbarrier, TMEM read,
 // two-pass LayerNorm}, sample, env step), four tiles overlap to 9,300.  Removing one part at a time (timing only)
