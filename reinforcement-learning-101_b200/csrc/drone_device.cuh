@@ -140,4 +140,37 @@ __device__ __forceinline__ void stats_warp_commit(unsigned long long* stats, uin
     }
 }
 
+// The same statistics accumulated PER THREAD over a multi-step kernel and committed once at its end: integer sums, so
+// the totals equal a stats_warp_commit per step.  (In the T-steps-per-launch kernels the per-step commit -- a ballot every
+// step; three more ballots, ten shuffles and six atomics whenever a lane's episode ended -- was 1-6 % of the issue slots.)
+struct StatsAcc {
+    uint32_t done = 0, landed = 0, crashed = 0, trunc = 0, len = 0;
+    long long ret = 0;
+    template <typename R>
+    __device__ __forceinline__ void add(uint32_t f, R ret_, int32_t steps) {
+        if (f) {
+            done += 1u; landed += (f & DD_LANDED) ? 1u : 0u; crashed += (f & DD_CRASHED) ? 1u : 0u; trunc += (f & DD_TRUNCATED) ? 1u : 0u;
+            ret += return_fx(ret_); len += (uint32_t)steps;
+        }
+    }
+    // called by ALL 32 lanes of a warp
+    __device__ __forceinline__ void commit(unsigned long long* stats) const {
+        const unsigned nd = __reduce_add_sync(0xffffffffu, done);
+        if (nd == 0u) return;                              // warp-uniform
+        const unsigned nl = __reduce_add_sync(0xffffffffu, landed), nc = __reduce_add_sync(0xffffffffu, crashed),
+                       nt = __reduce_add_sync(0xffffffffu, trunc);
+        const long long lsum = warp_sum_ll((long long)len), rsum = warp_sum_ll(ret);
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            unsigned long long* s = stats + (gw % DD_STATS_SLOTS) * DD_STATS_WORDS;
+            atomicAdd(s + 0, (unsigned long long)nd);
+            if (nl) atomicAdd(s + 1, (unsigned long long)nl);
+            if (nc) atomicAdd(s + 2, (unsigned long long)nc);
+            if (nt) atomicAdd(s + 3, (unsigned long long)nt);
+            atomicAdd(s + 4, (unsigned long long)rsum);
+            atomicAdd(s + 5, (unsigned long long)lsum);
+        }
+    }
+};
+
 }  // namespace dd

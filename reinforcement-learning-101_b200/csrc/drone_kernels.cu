@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
         dprev = a.prev_dist[i];
     }
 
+    StatsAcc st;                                             // per-thread statistics, one commit per warp and launch
     for (int32_t t = 0; t < ra.T; ++t) {
         uint32_t oflags = pflags, f_stat = 0;
         R ret_stat = 0; int32_t len_stat = 0;
@@ -272,13 +273,14 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                 if (a.obs_stride > DD_OBS_DIM) row[DD_OBS_DIM] = (R)e.steps;
             }
         }
-        if (do_stats) stats_warp_commit(a.stats, f_stat, ret_stat, len_stat);
+        if (do_stats) st.add(f_stat, ret_stat, len_stat);
         if (OBS) {
             obs_tile_store<R, kBlock>(s_obs, ra.obs_tn + ((size_t)t * a.n + tile0) * a.obs_stride, rows, a.obs_stride);
             __syncthreads();                                   // tile is reused next step
         }
     }
 
+    if (do_stats) st.commit(a.stats);
     if (live) {
         store_env(a, i, e);
         a.flags[i] = (uint8_t)pflags;

@@ -561,8 +561,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     // totals as a commit per step; the per-step warp commit -- a ballot every step, three more ballots, ten shuffles and six
     // atomics whenever a lane's episode ended, ~30 % of the warp-steps of a trained policy -- sat in the over-full shadow
     // of the first MMA, i.e. on the tile's chain: 1.173 -> 1.155 ms).
-    uint32_t st_done = 0, st_land = 0, st_crash = 0, st_trunc = 0, st_len = 0;
-    long long st_ret = 0;
+    StatsAcc st;
     struct Pending { float p0, p1, p2, reward, shaped, ret_stat; uint32_t act, oflags, f_stat; int32_t len_stat; } pend = {};
     auto flush_pending = [&](size_t o_prev) {
         if (DD_K5_ABLATE & 8) return;
@@ -580,11 +579,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             if (out_rew) pa.reward_tn[o_prev] = pend.reward;
             if (out_done) pa.done_tn[o_prev] = (uint8_t)pend.oflags;
         }
-        if (do_stats && pend.f_stat) {
-            st_done += 1u; st_land += (pend.f_stat & DD_LANDED) ? 1u : 0u; st_crash += (pend.f_stat & DD_CRASHED) ? 1u : 0u;
-            st_trunc += (pend.f_stat & DD_TRUNCATED) ? 1u : 0u;
-            st_ret += return_fx(pend.ret_stat); st_len += (uint32_t)pend.len_stat;
-        }
+        if (do_stats) st.add(pend.f_stat, pend.ret_stat, pend.len_stat);
     };
 
     for (int32_t t = 0; t < T_mine; ++t) {
@@ -838,25 +833,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         pend.oflags = oflags; pend.f_stat = f_stat; pend.ret_stat = ret_stat; pend.len_stat = len_stat;
     }
     if (!forward_only && T_mine > 0) flush_pending((size_t)(T_mine - 1) * a.n + i);
-    if (!forward_only && do_stats && T_mine > 0) {                               // one statistics commit per warp and rollout
-        const unsigned nd = __reduce_add_sync(0xffffffffu, st_done);
-        if (nd) {                                            // warp-uniform
-            const unsigned nl = __reduce_add_sync(0xffffffffu, st_land), nc = __reduce_add_sync(0xffffffffu, st_crash),
-                           nt = __reduce_add_sync(0xffffffffu, st_trunc);
-            const unsigned long long len = (unsigned long long)warp_sum_ll((long long)st_len);
-            const long long rsum = warp_sum_ll(st_ret);
-            if ((tid & 31) == 0) {
-                const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-                unsigned long long* sl = a.stats + (gw % DD_STATS_SLOTS) * DD_STATS_WORDS;
-                atomicAdd(sl + 0, (unsigned long long)nd);
-                if (nl) atomicAdd(sl + 1, (unsigned long long)nl);
-                if (nc) atomicAdd(sl + 2, (unsigned long long)nc);
-                if (nt) atomicAdd(sl + 3, (unsigned long long)nt);
-                atomicAdd(sl + 4, (unsigned long long)rsum);
-                atomicAdd(sl + 5, len);
-            }
-        }
-    }
+    if (!forward_only && do_stats && T_mine > 0) st.commit(a.stats);            // one statistics commit per warp and rollout
 
     if (live && !forward_only) {
         store4(a.pos_vel, i, e.x, e.y, e.vx, e.vy);
