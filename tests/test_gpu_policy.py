@@ -272,6 +272,31 @@ def test_full_size_cfg4_properties_and_shard_invariance(fixture):
     assert tot == {k_: s[k_] for k_ in tot}
 
 
+@pytest.mark.parametrize("n", [148 * 3 * 128, 148 * 3 * 128 + 128, 60000, 148 * 4 * 128 + 4])
+def test_launch_shapes_give_the_same_rollout(fixture, n):
+    """The launcher spreads the tiles over the SMs up to 3 per SM and packs four to a CTA above that
+    (dd_policy_rollout_grid); more than 4 tiles per SM run as waves.  Around those thresholds (and with a ragged last
+    tile that leaves by TMA) a rollout of n envs must contain, bit for bit, the rollout of any sub-range of its env ids
+    launched on its own (a small batch: one tile per CTA), observations included."""
+    d, sd = fixture
+    blob = dd.PolicyBlob(sd, device=DEV)
+    T = 24
+    kw = dict(seed=5, randomize_drone=True, randomize_platform=True, max_steps=20, auto_reset=True, dtype=torch.float32)
+    big = dd.BatchedDroneEnv(n, device=DEV, **kw); big.reset()
+    out = dd.policy_rollout(big, blob, T, sample=True, want="arldo")
+    L = nv.lib()
+    assert L.dd_policy_rollout_grid(n, 148) == (min(-(-n // 128), 148) if -(-n // 128) <= 3 * 148 else -(-n // 512))
+    for base, m in ((0, 1000), (n - 4096 - (n % 128), 4096), (n - 516, 516)):
+        sub = dd.BatchedDroneEnv(m, device=DEV, env_id_base=base, **kw); sub.reset()
+        o = dd.policy_rollout(sub, blob, T, sample=True, want="arldo")
+        for key in ("actions", "reward", "logp", "done"):
+            assert torch.equal(o[key], out[key][:, base:base + m]), (key, base, m)
+        assert torch.equal(o["obs"], out["obs"][:, base:base + m]), (base, m)
+    s = big.stats()
+    assert s["env_steps"] == n * T and s["episodes"] == s["landed"] + s["crashed"] + s["truncated"]
+    assert int((out["done"] != 0).sum().item()) == s["episodes"]
+
+
 @pytest.mark.parametrize("n", [1, 3, 130, 1001])
 def test_rollout_ragged_sizes_use_the_fallback_obs_store(fixture, n):
     """n not a multiple of 4 (or a partial last tile) cannot use the TMA bulk store of the observation tile:
