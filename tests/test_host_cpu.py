@@ -148,6 +148,52 @@ def test_policy_rollout_grid_covers_every_tile_once(lib):
     assert lib.dd_policy_rollout_grid(0, sms) == 0 and lib.dd_policy_rollout_grid(-5, sms) == 0
 
 
+def test_the_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may touch it.
+    Static check of every import statement of the package and of bench.py, plus a fresh interpreter that imports the
+    package and looks at sys.modules."""
+    import ast
+    pkg_dir = os.path.join(ROOT, "reinforcement-learning-101_b200")
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read(), path)
+        parents = {}
+        for node in ast.walk(tree):
+            for ch in ast.iter_child_nodes(node):
+                parents[ch] = node
+        found = []
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a_.name for a_ in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            if any(m == "oracle" or m.startswith("oracle.") or m == "tests" or m.startswith("tests.") for m in mods):
+                fn, cur = None, node
+                while cur in parents:
+                    cur = parents[cur]
+                    if isinstance(cur, ast.FunctionDef):
+                        fn = cur.name
+                        break
+                found.append(fn)
+        return found
+
+    for name in sorted(os.listdir(pkg_dir)):
+        if name.endswith(".py"):
+            assert oracle_imports(os.path.join(pkg_dir, name)) == [], name
+    for name in sorted(os.listdir(os.path.join(pkg_dir, "csrc"))):
+        includes = [l for l in open(os.path.join(pkg_dir, "csrc", name)).read().splitlines() if l.lstrip().startswith("#include")]
+        assert not any("oracle" in l or "tests/" in l for l in includes), name        # (comments may cite the oracle)
+    # bench.py: only inside the CPU-baseline legs (the reference arm and the cpu_baseline key)
+    assert set(oracle_imports(os.path.join(ROOT, "bench.py"))) <= {"cpu_port_multiprocess", "c_oracle_threads", "run_reference"}
+    code = ("import importlib, sys; sys.path.insert(0, %r); importlib.import_module('reinforcement-learning-101_b200'); "
+            "import importlib as _i; m = _i.import_module('reinforcement-learning-101_b200'); "
+            "[getattr(m, k) for k in ('BatchedDroneEnv', 'ShardedDroneEnv', 'policy_rollout', 'gae', 'curriculum_sweep', 'compat')]; "
+            "bad = [k for k in sys.modules if k == 'oracle' or k.startswith('oracle.')]; print('BAD' if bad else 'CLEAN', bad)" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "CLEAN" in out.stdout, out.stdout + out.stderr
+
+
 def test_shard_range_covers_all_ids():
     for total, ws in ((16, 1), (16, 8), (17, 4), (3, 8), (1 << 24, 8)):
         spans = [dd.shard_range(total, r, ws) for r in range(ws)]
