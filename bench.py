@@ -195,18 +195,21 @@ def _peaks_all():
 
 def _ncu_traffic(n: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of step_kernel<float,AUTO,OBS> from the COMMITTED
-    ncu capture (profiles/r01_traffic_steady.json; ncu cannot run inside the bench) -- a constant read from that file,
-    not measured in this run, and only valid for the launch size it was captured at."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_steady.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)
-        k = d["kernels"]["void step_kernel<float, 1, 1, 1, 256>(KArgs<T1>)"]
-        if d["algorithmic_bytes_per_launch"]["step_kernel<float,AUTO,OBS>"] != BYTES_GYM * n:
-            return None, f"profiles/r01_traffic_steady.json was captured at another launch size than {n} envs"
-        return k["dram_bytes_per_launch"], "constant from the committed capture profiles/r01_traffic_steady.json (ncu, steady state, --cache-control none); not measured in this run"
-    except (OSError, KeyError, ValueError):
-        return None, "no ncu capture committed"
+    ncu capture (the newest of profiles/r02_traffic_steady.json, r01_traffic_steady.json; ncu cannot run inside the
+    bench) -- a constant read from that file, not measured in this run, and only valid for the launch size it was
+    captured at."""
+    for name in ("r02_traffic_steady.json", "r01_traffic_steady.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            k = next(v for kk, v in d["kernels"].items() if "step_kernel<float, 1, 1, 1, 256>" in kk)
+            if d["algorithmic_bytes_per_launch"]["step_kernel<float,AUTO,OBS>"] != BYTES_GYM * n:
+                return None, f"profiles/{name} was captured at another launch size than {n} envs"
+            return k["dram_bytes_per_launch"], f"constant from the committed capture profiles/{name} (ncu, steady state, --cache-control none); not measured in this run"
+        except (OSError, KeyError, ValueError, StopIteration):
+            continue
+    return None, "no ncu capture committed"
 
 
 def socket_shim_rate(dev, games: int = 6, seconds: float = 2.0):
