@@ -528,6 +528,19 @@ def run_ours(args):
             ach = ne * bytes_el / (ms_ * 1e-3) / 1e9
             others[name] = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                             "ms_per_launch": ms_, "elements": ne, "algorithmic_bytes_per_element": bytes_el, "what": what}
+        # The figures above are taken in pipeline order, back to back, on a board that the 40-launch loops of the tensor
+        # kernels have driven into its power cap (SM clock ~1.7-1.8 GHz).  For reference, the same two kernels again after
+        # 0.4 s of idle, i.e. from the boost clock a PPO loop sees when its rollout follows a learning phase (not used for
+        # any headline number; the clock-sensitive ones are K5 itself and the GAE scan, 443 threads per SM).
+        torch.cuda.synchronize(dev); time.sleep(0.4)
+        ms_g_idle = timed(lambda: t_gae(4), lambda: t_gae(n_g)) / n_g
+        torch.cuda.synchronize(dev); time.sleep(0.4)
+        ms_pol_idle = timed(lambda: run_policy(2), lambda: run_policy(20)) / 20
+        launches += n_g + 4 + 22
+        others["gae_kernel"].update({"ms_per_launch_after_idle": ms_g_idle, "frac_after_idle": ne * (13.0 + 4.0 / TP) / (ms_g_idle * 1e-3) / 1e9 / peak_gbs})
+        others["fused_policy_rollout_K5"].update({"ms_per_launch_after_idle": ms_pol_idle,
+                                                  "frac_after_idle": NP * TP * FLOP_STEP / (ms_pol_idle * 1e-3) / 1e12 / PK["bf16_sustained"],
+                                                  "after_idle_what": "the same launch timed again (20 launches) after 0.4 s of idle: boost clock instead of the power-capped clock the preceding timing loops leave"})
         del rot, nrm_out
         # the same through HOST-side inputs / outputs, as one PPO iteration sees it: policy + critic weights come from
         # host state_dicts (packed and uploaded every iteration, like after an optimiser step), the rollout buffers
