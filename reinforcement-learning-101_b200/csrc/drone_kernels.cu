@@ -220,8 +220,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
 
     StatsAcc st;                                             // per-thread statistics, one commit per warp and launch
     for (int32_t t = 0; t < ra.T; ++t) {
-        uint32_t oflags = pflags, f_stat = 0;
-        R ret_stat = 0; int32_t len_stat = 0;
+        uint32_t oflags = pflags;
         R reward = (R)0, speed = (R)0, dist = (R)0, shaped = (R)0;
         if (live) {
             const size_t o = (size_t)t * a.n + i;
@@ -250,7 +249,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                     dcur = Arith<R>::div(dist, k.width, k.inv_width);
                 }
                 if (f) {
-                    f_stat = f; ret_stat = e.ret; len_stat = e.steps;
+                    if (do_stats) st.add(f, e.ret, e.steps);          // per-thread totals, committed once after the loop
                     if (auto_reset) {
                         spawn(e, k, a.seed, gid, ep, a.rand_drone != 0, a.rand_platform != 0);
                         ep += 1;
@@ -273,7 +272,6 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
                 if (a.obs_stride > DD_OBS_DIM) row[DD_OBS_DIM] = (R)e.steps;
             }
         }
-        if (do_stats) st.add(f_stat, ret_stat, len_stat);
         if (OBS) {
             obs_tile_store<R, kBlock>(s_obs, ra.obs_tn + ((size_t)t * a.n + tile0) * a.obs_stride, rows, a.obs_stride);
             __syncthreads();                                   // tile is reused next step
