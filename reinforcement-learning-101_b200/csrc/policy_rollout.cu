@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
     // atomics whenever a lane's episode ended, ~30 % of the warp-steps of a trained policy -- sat in the over-full shadow
     // of the first MMA, i.e. on the tile's chain: 1.173 -> 1.155 ms).
     StatsAcc st;
-    struct Pending { float p0, p1, p2, reward, shaped, ret_stat; uint32_t act, oflags, f_stat; int32_t len_stat; } pend = {};
+    struct Pending { float p0, p1, p2, reward, shaped; uint32_t act, oflags; } pend = {};
     auto flush_pending = [&](size_t o_prev) {
         if (DD_K5_ABLATE & 8) return;
         if (live) {
@@ -579,7 +579,6 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             if (out_rew) pa.reward_tn[o_prev] = pend.reward;
             if (out_done) pa.done_tn[o_prev] = (uint8_t)pend.oflags;
         }
-        if (do_stats) st.add(pend.f_stat, pend.ret_stat, pend.len_stat);
     };
 
     for (int32_t t = 0; t < T_mine; ++t) {
@@ -803,8 +802,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
         }
 
         // ---------------- environment step (same code as K1) -------------------------------------------
-        uint32_t oflags = pflags, f_stat = 0;
-        float ret_stat = 0; int32_t len_stat = 0;
+        uint32_t oflags = pflags;
         float reward = 0.f, shaped = 0.f;
         if (live && !(pflags & DD_DONE) && !(DD_K5_ABLATE & 2)) {
             uint32_t f = step_core<float, true, true>(e, act, k, reward, speed, dist, s_pre, c_pre);
@@ -816,7 +814,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
                 dcur = Arith<float>::div(dist, k.width, k.inv_width);
             }
             if (f) {
-                f_stat = f; ret_stat = e.ret; len_stat = e.steps;
+                if (do_stats) st.add(f, e.ret, e.steps);     // per-thread totals (a few predicated adds in the episode-end branch)
                 if (auto_reset) {
                     spawn_apply(e, k, nsx, nsy, nspx, nspy);                   // == spawn(e, ..., ep): drawn ahead of time
                     ep += 1;
@@ -830,7 +828,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_rollout_kernel(const __
             pflags = f;
         }
         pend.p0 = p0; pend.p1 = p1; pend.p2 = p2; pend.act = act; pend.reward = reward; pend.shaped = shaped;
-        pend.oflags = oflags; pend.f_stat = f_stat; pend.ret_stat = ret_stat; pend.len_stat = len_stat;
+        pend.oflags = oflags;
     }
     if (!forward_only && T_mine > 0) flush_pending((size_t)(T_mine - 1) * a.n + i);
     if (!forward_only && do_stats && T_mine > 0) st.commit(a.stats);            // one statistics commit per warp and rollout
