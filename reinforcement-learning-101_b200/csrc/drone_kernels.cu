@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     }
 
     StatsAcc st;                                             // per-thread statistics, one commit per warp and launch
-    for (int32_t t = 0; t < ra.T; ++t) {
+    auto one_step = [&](const int32_t t) {
         uint32_t oflags = pflags;
         R reward = (R)0, speed = (R)0, dist = (R)0, shaped = (R)0;
         if (live) {
@@ -228,13 +228,8 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
             if (POLICY == DD_POLICY_TRACE) {
                 act = ra.actions_tn[o];
             } else if (POLICY == DD_POLICY_RANDOM) {
-                if ((tt & 31u) == 0u && t > 0) {
-                    const U4 b = action_block(a.seed, gid, tt);
-                    rb0 = b.a; rb1 = b.b; rb2 = b.c;
-                }
                 act = rb0 & 7u;
                 rb0 = __funnelshift_r(rb0, rb1, 3); rb1 = __funnelshift_r(rb1, rb2, 3); rb2 >>= 3;
-                ++tt;
             } else {
                 act = (e.vy > (R)1.5) ? DD_ACT_MAIN : 0u;
             }
@@ -276,6 +271,22 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
             obs_tile_store<R, kBlock>(s_obs, ra.obs_tn + ((size_t)t * a.n + tile0) * a.obs_stride, rows, a.obs_stride);
             __syncthreads();                                   // tile is reused next step
         }
+    };
+    if constexpr (POLICY == DD_POLICY_RANDOM) {
+        // the steps are walked block by block (32 steps = one action_block): the refill of the shift register sits between
+        // the blocks instead of behind a test in every step
+        for (int32_t t = 0; t < ra.T;) {
+            if (t > 0) {                                     // (tt & 31) == 0 here: the next block
+                const U4 b = action_block(a.seed, gid, tt);
+                rb0 = b.a; rb1 = b.b; rb2 = b.c;
+            }
+            const int32_t left = 32 - (int32_t)(tt & 31u);
+            const int32_t t_end = ra.T - t < left ? ra.T : t + left;
+            tt += (uint32_t)(t_end - t);
+            for (; t < t_end; ++t) one_step(t);
+        }
+    } else {
+        for (int32_t t = 0; t < ra.T; ++t) one_step(t);
     }
 
     if (do_stats) st.commit(a.stats);
